@@ -1,0 +1,143 @@
+// b200_api.cpp — extension entry points declared in include/b200_engine.h (measurement, plan
+// inspection, parity debugging).  Not part of the reference ABI.
+#include "b200_engine.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <future>
+#include <memory>
+#include <string>
+
+#include "engine.h"
+#include "kernels.h"
+#include "model.h"
+#include "model_impl.h"
+#include "onnx_wire.h"
+#include "plan.h"
+
+std::shared_ptr<inference::Model> B200ModelFromHandle(ModelHandle h);
+
+namespace {
+void SetErr(ErrorMessage* error, const std::string& msg) {
+    if (error) *error = strdup(msg.c_str());
+}
+std::shared_ptr<inference::ModelImpl::Loaded> PinHandle(ModelHandle h, std::shared_ptr<inference::Model>* keep, ErrorMessage* error) {
+    *keep = B200ModelFromHandle(h);
+    if (!*keep) {
+        SetErr(error, "Invalid model handle");
+        return nullptr;
+    }
+    auto st = (*keep)->Impl()->Pin();
+    if (!st) SetErr(error, "Model not loaded");
+    return st;
+}
+}  // namespace
+
+extern "C" {
+
+const char* B200EngineVersion(void) { return "b200-engine 0.1 sm_100a"; }
+
+char* B200PlanDescribe(const char* model_dir, const char* precision, int max_batch, ErrorMessage* error) {
+    try {
+        if (!model_dir) throw std::runtime_error("model_dir is null");
+        b200::Precision p = b200::Precision::FP32;
+        if (precision && !b200::ParsePrecision(precision, &p)) throw std::runtime_error(std::string("unknown precision '") + precision + "'");
+        b200::onnx::Model m = b200::onnx::ParseFile(std::string(model_dir) + "/model.onnx");
+        b200::Plan plan = b200::BuildPlan(m, p, max_batch > 0 ? max_batch : 256);
+        return strdup(plan.ToJson().c_str());
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return nullptr;
+    }
+}
+
+uint64_t B200KernelLaunchCount(void) { return b200::kernels::LaunchCount(); }
+
+bool B200ModelStageInput(ModelHandle handle, const TensorData* input, ErrorMessage* error) {
+    std::shared_ptr<inference::Model> keep;
+    auto st = PinHandle(handle, &keep, error);
+    if (!st) return false;
+    try {
+        if (!input || !input->data || !input->shape.dims || input->shape.num_dims < 1) throw std::runtime_error("Invalid parameters");
+        const b200::Plan& P = *st->plan;
+        int idx = -1;
+        for (size_t i = 0; i < P.input_names.size(); ++i)
+            if (input->name && P.input_names[i] == input->name) idx = (int)i;
+        if (idx < 0) throw std::runtime_error(std::string("Unexpected input name: ") + (input->name ? input->name : ""));
+        int n = (int)input->shape.dims[0];
+        const auto& t = P.tensors[P.inputs[idx]];
+        if (n < 1 || n > P.max_batch) throw std::runtime_error("batch exceeds B200_ENGINE_MAX_BATCH");
+        if (input->data_size < (size_t)n * t.C * t.H * t.W * 4) throw std::runtime_error("Invalid FLOAT32 data for input");
+        for (auto& r : st->replicas) r->StageInput(idx, input->data, n);
+        keep->Impl()->staged_batch = n;
+        return true;
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return false;
+    }
+}
+
+bool B200ModelForwardDevice(ModelHandle handle, int batch, int iters, int l2_flush, float* ms_out, ErrorMessage* error) {
+    std::shared_ptr<inference::Model> keep;
+    auto st = PinHandle(handle, &keep, error);
+    if (!st) return false;
+    try {
+        if (batch < 1 || batch > st->plan->max_batch || iters < 1 || !ms_out) throw std::runtime_error("Invalid parameters");
+        for (int it = 0; it < iters; ++it) {
+            std::vector<std::future<float>> futs;
+            for (size_t g = 1; g < st->replicas.size(); ++g) {
+                b200::Replica* r = st->replicas[g].get();
+                futs.push_back(std::async(std::launch::async, [r, batch, l2_flush] { return r->ForwardTimed(batch, l2_flush != 0); }));
+            }
+            float ms = st->replicas[0]->ForwardTimed(batch, l2_flush != 0);
+            for (auto& f : futs) ms = std::max(ms, f.get());
+            ms_out[it] = ms;
+        }
+        return true;
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return false;
+    }
+}
+
+bool B200ModelReadOutput(ModelHandle handle, float* out, size_t out_elems, ErrorMessage* error) {
+    std::shared_ptr<inference::Model> keep;
+    auto st = PinHandle(handle, &keep, error);
+    if (!st) return false;
+    try {
+        st->replicas[0]->ReadOutput(0, out, out_elems * 4);
+        return true;
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return false;
+    }
+}
+
+char* B200ModelProfileSteps(ModelHandle handle, int batch, int repeats, ErrorMessage* error) {
+    std::shared_ptr<inference::Model> keep;
+    auto st = PinHandle(handle, &keep, error);
+    if (!st) return nullptr;
+    try {
+        return strdup(st->replicas[0]->ProfileSteps(batch, repeats).c_str());
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return nullptr;
+    }
+}
+
+int64_t B200ModelReadValue(ModelHandle handle, const char* value_name, float* out, size_t out_elems, ErrorMessage* error) {
+    std::shared_ptr<inference::Model> keep;
+    auto st = PinHandle(handle, &keep, error);
+    if (!st) return -1;
+    try {
+        int n = keep->Impl()->staged_batch > 0 ? keep->Impl()->staged_batch : 1;
+        int64_t r = st->replicas[0]->ReadValue(value_name ? value_name : "", out, out_elems, n);
+        if (r < 0) SetErr(error, "unknown value name or insufficient capacity");
+        return r;
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return -1;
+    }
+}
+
+}  // extern "C"

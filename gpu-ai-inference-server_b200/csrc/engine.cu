@@ -1,0 +1,403 @@
+// engine.cu — Replica: executes a Plan on one GPU.  Replaces `Ort::Session::Run`
+// (reference inference_engine/src/model.cpp:1264-1270) and the host<->device traffic that lives
+// inside ONNX Runtime's CUDA EP in the reference.
+#include "engine.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+namespace b200 {
+
+void CudaCheck(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        std::string msg = std::string("CUDA error in ") + what + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+        throw CudaError(msg);
+    }
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        CudaCheck(cudaSetDevice(dev), "cudaSetDevice");
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn GetEncodeTiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    if (!fn) throw CudaError("cuTensorMapEncodeTiled is not available from this driver");
+    return fn;
+}
+
+uint16_t F32ToBf16(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u && (u & 0x7FFFFFu)) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    u += 0x7FFFu + ((u >> 16) & 1u);  // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------
+Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
+    : device_(device), plan_(std::move(plan)), use_graphs_(use_graphs) {
+    DeviceGuard g(device_);
+    cudaDeviceProp prop;
+    CudaCheck(cudaGetDeviceProperties(&prop, device_), "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        throw CudaError("device " + std::to_string(device_) + " (" + prop.name + ", sm_" + std::to_string(prop.major) +
+                        std::to_string(prop.minor) + ") is not a Blackwell sm_100 GPU; this engine ships sm_100a code only");
+    }
+    CudaCheck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    CudaCheck(cudaEventCreate(&ev0_), "cudaEventCreate");
+    CudaCheck(cudaEventCreate(&ev1_), "cudaEventCreate");
+    CudaCheck(cudaMalloc((void**)&arena_, plan_->arena_bytes + 4096), "cudaMalloc(arena)");
+    CudaCheck(cudaMemsetAsync(arena_, 0, plan_->arena_bytes + 4096, stream_), "cudaMemset(arena)");
+    device_bytes_ += plan_->arena_bytes + 4096;
+
+    const Plan& P = *plan_;
+    // fp32 device copies of per-channel vectors, uploaded lazily below
+    dconst_.assign(P.consts.size(), nullptr);
+    auto vec = [&](int idx) -> const float* {
+        if (idx < 0) return nullptr;
+        if (!dconst_[idx]) dconst_[idx] = (const float*)Upload(P.consts[idx].data.data(), P.consts[idx].data.size() * 4);
+        return dconst_[idx];
+    };
+
+    prepared_.resize(P.steps.size());
+    for (size_t i = 0; i < P.steps.size(); ++i) {
+        const Step& s = P.steps[i];
+        Prepared& pr = prepared_[i];
+        if (s.in >= 0) pr.in = MakeView(s.in);
+        if (s.in2 >= 0) pr.in2 = MakeView(s.in2);
+        if (s.out >= 0) pr.out = MakeView(s.out);
+        pr.scale = vec(s.bn_scale);
+        pr.shift = vec(s.bn_shift);
+        if (s.kind != StepKind::Conv) continue;
+
+        kernels::ConvArgs& a = pr.conv;
+        a.in = pr.in;
+        a.out = pr.out;
+        a.R = s.R; a.S = s.S; a.stride = s.stride; a.pad = s.pad;
+        a.Cin = s.Cin; a.Cout = s.Cout;
+        a.pre_scale = vec(s.pre_scale);
+        a.pre_shift = vec(s.pre_shift);
+        a.pre_relu = s.pre_relu;
+        a.bias = vec(s.bias);
+        a.post_relu = s.post_relu;
+        a.pool2 = s.pool2_fused;
+        const std::vector<float>& w = P.consts[s.weight].data;  // [Cout][R][S][Cin]
+        const int K = s.R * s.S * s.Cin;
+        pr.use_umma = pr.in.dtype != DType::F32;
+        if (!pr.use_umma) {
+            std::vector<float> kn((size_t)K * s.Cout);
+            for (int o = 0; o < s.Cout; ++o)
+                for (int k = 0; k < K; ++k) kn[(size_t)k * s.Cout + o] = w[(size_t)o * K + k];
+            pr.w_kn = (const float*)Upload(kn.data(), kn.size() * 4);
+            continue;
+        }
+        // ---- tcgen05 path: [Cout_pad][K_pad] K-major in the MMA element type ----
+        if (!kernels::UmmaSupported(a))
+            throw CudaError("conv '" + s.name + "' has a shape the tcgen05 path does not support in " +
+                            PrecisionName(P.precision) + " mode (Cin=" + std::to_string(s.Cin) + ", Cout=" + std::to_string(s.Cout) + ")");
+        const DType mt = pr.in.dtype;
+        const int esz = (int)DTypeSize(mt);
+        const int kc = kernels::UmmaKChunkElems(mt);
+        const int cin_pad = kernels::UmmaPaddedCin(s.Cin, s.R, s.S, mt);
+        const bool stem = s.Cin < 16;
+        // stem packing: k = r*32 + s*4 + c (8 pixels x 4 channels per filter row, zero padded)
+        const int K_pad = stem ? ((s.R * 32 + kc - 1) / kc * kc) : s.R * s.S * cin_pad;
+        const int bn = s.Cout <= 32 ? 32 : s.Cout <= 64 ? 64 : 128;
+        const int cout_pad = (s.Cout + bn - 1) / bn * bn;
+        std::vector<float> scale(s.Cout, 1.f);
+        if (mt == DType::FP8) {
+            for (int o = 0; o < s.Cout; ++o) {
+                float amax = 0.f;
+                for (int k = 0; k < K; ++k) amax = std::max(amax, std::fabs(w[(size_t)o * K + k]));
+                scale[o] = amax > 0.f ? amax / 448.f : 1.f;
+            }
+        }
+        std::vector<uint8_t> packed((size_t)cout_pad * K_pad * esz, 0);
+        auto put = [&](int o, int kk, float v) {
+            size_t idx = (size_t)o * K_pad + kk;
+            if (mt == DType::BF16) {
+                uint16_t h = F32ToBf16(v);
+                memcpy(&packed[idx * 2], &h, 2);
+            } else {
+                __nv_fp8_e4m3 q(v / scale[o]);
+                memcpy(&packed[idx], &q, 1);
+            }
+        };
+        for (int o = 0; o < s.Cout; ++o)
+            for (int r = 0; r < s.R; ++r)
+                for (int ss = 0; ss < s.S; ++ss)
+                    for (int c = 0; c < s.Cin; ++c) {
+                        float v = w[(((size_t)o * s.R + r) * s.S + ss) * s.Cin + c];
+                        int kk = stem ? r * 32 + ss * 4 + c : (r * s.S + ss) * cin_pad + c;
+                        put(o, kk, v);
+                    }
+        pr.umma.w = Upload(packed.data(), packed.size());
+        pr.umma.out_scale = (const float*)Upload(scale.data(), scale.size() * 4);
+        pr.umma.K_pad = K_pad;
+        pr.umma.Cout_pad = cout_pad;
+        // TMA descriptor over the packed weights: dims {K_pad, Cout_pad}, box {kc, bn}, 128-byte swizzle
+        CUtensorMap* tm = new CUtensorMap;
+        cuuint64_t dims[2] = {(cuuint64_t)K_pad, (cuuint64_t)cout_pad};
+        cuuint64_t strides[1] = {(cuuint64_t)K_pad * esz};
+        cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = GetEncodeTiled()(tm, mt == DType::BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                                      const_cast<void*>(pr.umma.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            delete tm;
+            throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for conv '" + s.name + "'");
+        }
+        pr.umma.tensor_map = tm;
+    }
+    flush_bytes_ = 256u << 20;
+    CudaCheck(cudaStreamSynchronize(stream_), "replica init");
+}
+
+Replica::~Replica() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
+    for (auto& pr : prepared_)
+        if (pr.umma.tensor_map) delete (CUtensorMap*)pr.umma.tensor_map;
+    for (void* p : allocations_) cudaFree(p);
+    if (flush_buf_) cudaFree(flush_buf_);
+    if (arena_) cudaFree(arena_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void* Replica::Upload(const void* host, size_t bytes) {
+    void* d = nullptr;
+    size_t padded = (bytes + 255) / 256 * 256 + 256;
+    CudaCheck(cudaMalloc(&d, padded), "cudaMalloc(weights)");
+    allocations_.push_back(d);
+    device_bytes_ += padded;
+    CudaCheck(cudaMemsetAsync(d, 0, padded, stream_), "cudaMemset(weights)");
+    CudaCheck(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, stream_), "cudaMemcpy(weights)");
+    CudaCheck(cudaStreamSynchronize(stream_), "upload sync");
+    return d;
+}
+
+void* Replica::BufferPtr(int buffer) const { return arena_ + plan_->buffers[buffer].offset; }
+
+kernels::View Replica::MakeView(int tensor) const {
+    const TensorDesc& t = plan_->tensors[tensor];
+    kernels::View v;
+    v.base = BufferPtr(t.buffer);
+    v.dtype = t.dtype;
+    v.C = t.C; v.H = t.H; v.W = t.W;
+    v.pitch = t.pitch; v.c_off = t.c_off;
+    return v;
+}
+
+void Replica::EnqueueStep(size_t i, int n) {
+    const Step& s = plan_->steps[i];
+    Prepared& pr = prepared_[i];
+    cudaError_t e = cudaSuccess;
+    switch (s.kind) {
+        case StepKind::NchwToNhwc: e = kernels::NchwToNhwc((const float*)pr.in.base, pr.out, n, stream_); break;
+        case StepKind::NhwcToNchw: e = kernels::NhwcToNchw(pr.in, (float*)pr.out.base, n, stream_); break;
+        case StepKind::Conv: {
+            kernels::ConvArgs a = pr.conv;
+            a.n = n;
+            e = pr.use_umma ? kernels::ConvUmma(a, pr.umma, stream_) : kernels::ConvSimtF32(a, pr.w_kn, stream_);
+            break;
+        }
+        case StepKind::MaxPool: e = kernels::MaxPool(pr.in, pr.out, n, s.R, s.stride, s.pad, stream_); break;
+        case StepKind::AvgPool: e = kernels::AvgPool(pr.in, pr.out, n, s.R, s.stride, s.pad, s.count_include_pad, stream_); break;
+        case StepKind::BnRelu: e = kernels::BnRelu(pr.in, pr.out, n, pr.scale, pr.shift, s.relu, stream_); break;
+        case StepKind::GlobalAvgPool:
+            e = kernels::GlobalAvgPool(pr.in, (float*)pr.out.base + pr.out.c_off, pr.out.pitch, n, pr.scale, pr.shift, s.relu, stream_);
+            break;
+        case StepKind::Add: e = kernels::AddTensors(pr.in, pr.in2, pr.out, n, stream_); break;
+        case StepKind::Relu: e = kernels::ReluTensor(pr.in, pr.out, n, stream_); break;
+        case StepKind::Softmax:
+            e = kernels::SoftmaxRows((const float*)pr.in.base, (float*)pr.out.base, n, pr.in.C, stream_);
+            break;
+        case StepKind::CopyChannels: e = kernels::CopyChannels(pr.in, pr.out, n, stream_); break;
+    }
+    if (e != cudaSuccess) CudaCheck(e, ("step '" + s.name + "' (" + StepKindName(s.kind) + ")").c_str());
+}
+
+void Replica::Enqueue(int n) {
+    if (n <= 0 || n > plan_->max_batch) throw CudaError("batch " + std::to_string(n) + " exceeds the planned maximum");
+    if (!use_graphs_) {
+        for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n);
+        return;
+    }
+    auto it = graphs_.find(n);
+    if (it == graphs_.end()) {
+        cudaGraph_t graph = nullptr;
+        uint64_t before = kernels::LaunchCount();
+        CudaCheck(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+        try {
+            for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n);
+        } catch (...) {
+            cudaStreamEndCapture(stream_, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        CudaCheck(cudaStreamEndCapture(stream_, &graph), "cudaStreamEndCapture");
+        launches_per_forward_ = (int)(kernels::LaunchCount() - before);
+        kernels::CountLaunch(-launches_per_forward_);  // capture does not execute anything
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CudaCheck(e, "cudaGraphInstantiate");
+        if (graphs_.size() >= 64) {  // bound the cache
+            cudaGraphExecDestroy(graphs_.begin()->second);
+            graphs_.erase(graphs_.begin());
+        }
+        it = graphs_.emplace(n, exec).first;
+        graph_launches_[n] = launches_per_forward_;
+    }
+    CudaCheck(cudaGraphLaunch(it->second, stream_), "cudaGraphLaunch");
+    kernels::CountLaunch(graph_launches_[n]);
+}
+
+void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
+                  const std::vector<size_t>& out_capacity_bytes) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DeviceGuard g(device_);
+    const Plan& P = *plan_;
+    for (size_t i = 0; i < P.inputs.size(); ++i) {
+        const TensorDesc& t = P.tensors[P.inputs[i]];
+        size_t bytes = (size_t)n * t.C * t.H * t.W * 4;
+        CudaCheck(cudaMemcpyAsync(BufferPtr(t.buffer), host_inputs[i], bytes, cudaMemcpyHostToDevice, stream_), "H2D input");
+    }
+    Enqueue(n);
+    for (size_t i = 0; i < P.outputs.size() && i < host_outputs.size(); ++i) {
+        const TensorDesc& t = P.tensors[P.outputs[i]];
+        size_t bytes = std::min((size_t)n * t.C * t.H * t.W * 4, out_capacity_bytes[i]);
+        if (host_outputs[i] && bytes)
+            CudaCheck(cudaMemcpyAsync(host_outputs[i], BufferPtr(t.buffer), bytes, cudaMemcpyDeviceToHost, stream_), "D2H output");
+    }
+    CudaCheck(cudaStreamSynchronize(stream_), "forward");
+}
+
+void Replica::StageInput(int input_index, const void* host, int n) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DeviceGuard g(device_);
+    const TensorDesc& t = plan_->tensors[plan_->inputs.at(input_index)];
+    size_t bytes = (size_t)n * t.C * t.H * t.W * 4;
+    CudaCheck(cudaMemcpyAsync(BufferPtr(t.buffer), host, bytes, cudaMemcpyHostToDevice, stream_), "H2D stage");
+    CudaCheck(cudaStreamSynchronize(stream_), "stage sync");
+}
+
+float Replica::ForwardTimed(int n, bool flush_l2) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DeviceGuard g(device_);
+    if (flush_l2) {
+        if (!flush_buf_) CudaCheck(cudaMalloc(&flush_buf_, flush_bytes_), "cudaMalloc(flush)");
+        CudaCheck(kernels::FlushL2(flush_buf_, flush_bytes_, stream_), "flush L2");
+    }
+    CudaCheck(cudaEventRecord(ev0_, stream_), "event record");
+    Enqueue(n);
+    CudaCheck(cudaEventRecord(ev1_, stream_), "event record");
+    CudaCheck(cudaEventSynchronize(ev1_), "event sync");
+    float ms = 0.f;
+    CudaCheck(cudaEventElapsedTime(&ms, ev0_, ev1_), "event elapsed");
+    return ms;
+}
+
+void Replica::ReadOutput(int output_index, void* host, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DeviceGuard g(device_);
+    const TensorDesc& t = plan_->tensors[plan_->outputs.at(output_index)];
+    CudaCheck(cudaMemcpyAsync(host, BufferPtr(t.buffer), bytes, cudaMemcpyDeviceToHost, stream_), "D2H read");
+    CudaCheck(cudaStreamSynchronize(stream_), "read sync");
+}
+
+std::string Replica::ProfileSteps(int n, int repeats) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DeviceGuard g(device_);
+    const Plan& P = *plan_;
+    size_t ns = P.steps.size();
+    std::vector<cudaEvent_t> ev(ns + 1);
+    for (auto& e : ev) CudaCheck(cudaEventCreate(&e), "cudaEventCreate");
+    std::vector<double> ms(ns, 0.0);
+    repeats = std::max(1, repeats);
+    for (int r = 0; r < repeats + 1; ++r) {  // first pass is warm-up
+        CudaCheck(cudaEventRecord(ev[0], stream_), "event");
+        for (size_t i = 0; i < ns; ++i) {
+            EnqueueStep(i, n);
+            CudaCheck(cudaEventRecord(ev[i + 1], stream_), "event");
+        }
+        CudaCheck(cudaStreamSynchronize(stream_), "profile sync");
+        if (r == 0) continue;
+        for (size_t i = 0; i < ns; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+            ms[i] += t;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    std::ostringstream os;
+    os.precision(9);
+    os << "[";
+    for (size_t i = 0; i < ns; ++i) {
+        const Step& s = P.steps[i];
+        if (i) os << ",";
+        os << "{\"step\":" << i << ",\"kind\":\"" << StepKindName(s.kind) << "\",\"name\":\"";
+        for (char c : s.name) os << ((c == '"' || c == '\\') ? '_' : c);
+        os << "\",\"ms\":" << ms[i] / repeats << ",\"flops\":" << s.flops * n << ",\"bytes\":" << s.bytes * n
+           << ",\"umma\":" << (prepared_[i].use_umma ? "true" : "false");
+        if (s.kind == StepKind::Conv)
+            os << ",\"Cin\":" << s.Cin << ",\"Cout\":" << s.Cout << ",\"R\":" << s.R << ",\"H\":" << P.tensors[s.out].H;
+        os << "}";
+    }
+    os << "]";
+    return os.str();
+}
+
+int64_t Replica::ReadValue(const std::string& value_name, float* out, size_t capacity, int n) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DeviceGuard g(device_);
+    auto it = plan_->value_to_tensor.find(value_name);
+    if (it == plan_->value_to_tensor.end()) return -1;
+    const TensorDesc& t = plan_->tensors[it->second];
+    size_t elems = (size_t)n * t.C * t.H * t.W;
+    if (elems > capacity) return -1;
+    float* d = nullptr;
+    CudaCheck(cudaMalloc((void**)&d, elems * 4 + 16), "cudaMalloc(read value)");
+    cudaError_t e = kernels::NhwcToNchw(MakeView(it->second), d, n, stream_);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, elems * 4, cudaMemcpyDeviceToHost, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    cudaFree(d);
+    CudaCheck(e, "read value");
+    return (int64_t)elems;
+}
+
+}  // namespace b200

@@ -1,0 +1,84 @@
+// engine.h — per-GPU executor of a Plan ("replica"): weight replica, activation arena, stream,
+// CUDA-graph cache.  One Replica per visible GPU; batches are sharded across replicas with no
+// collective (images are independent, weights replicated) — SURVEY.md §8e.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "plan.h"
+
+namespace b200 {
+
+struct CudaError : public std::runtime_error {
+    explicit CudaError(const std::string& m) : std::runtime_error(m) {}
+};
+void CudaCheck(cudaError_t e, const char* what);
+
+class Replica {
+public:
+    Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs);
+    ~Replica();
+    Replica(const Replica&) = delete;
+    Replica& operator=(const Replica&) = delete;
+
+    int device() const { return device_; }
+    size_t DeviceBytes() const { return device_bytes_; }
+    const Plan& plan() const { return *plan_; }
+
+    // Host-to-host forward of `n` samples (n <= plan.max_batch): H2D of every graph input, all steps,
+    // D2H of every graph output (min(capacity, produced) bytes each).  Blocking.  Thread-safe (serialised).
+    void Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
+             const std::vector<size_t>& out_capacity_bytes);
+
+    // Measurement helpers (extension API).
+    void StageInput(int input_index, const void* host, int n);
+    float ForwardTimed(int n, bool flush_l2);  // ms between events on this replica's stream
+    void ReadOutput(int output_index, void* host, size_t bytes);
+    std::string ProfileSteps(int n, int repeats);
+    int64_t ReadValue(const std::string& value_name, float* out, size_t capacity, int n);
+
+    std::mutex& mutex() { return mu_; }
+
+private:
+    struct Prepared {
+        kernels::ConvArgs conv;        // Conv
+        const float* w_kn = nullptr;   // SIMT weights
+        kernels::UmmaWeights umma;     // tcgen05 weights
+        bool use_umma = false;
+        kernels::View in, in2, out;
+        const float* scale = nullptr;
+        const float* shift = nullptr;
+    };
+
+    void Enqueue(int n);            // every step on stream_ (captured into a graph when enabled)
+    void EnqueueStep(size_t i, int n);
+    kernels::View MakeView(int tensor) const;
+    void* BufferPtr(int buffer) const;
+    void* Upload(const void* host, size_t bytes);
+
+    int device_;
+    std::shared_ptr<const Plan> plan_;
+    bool use_graphs_;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    char* arena_ = nullptr;
+    void* flush_buf_ = nullptr;
+    size_t flush_bytes_ = 0;
+    std::vector<void*> allocations_;
+    std::vector<const float*> dconst_;  // fp32 device copy of every Plan::consts entry that is used as a vector
+    std::vector<Prepared> prepared_;
+    std::map<int, cudaGraphExec_t> graphs_;
+    std::map<int, int> graph_launches_;  // kernels per captured forward, for the launch counter
+    int launches_per_forward_ = 0;
+    size_t device_bytes_ = 0;
+    std::mutex mu_;
+};
+
+}  // namespace b200

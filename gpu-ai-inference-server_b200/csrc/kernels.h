@@ -1,0 +1,73 @@
+// kernels.h — host-callable launchers of the engine's CUDA kernels (sm_100a only).
+// All pointers are device pointers; every launcher enqueues on `stream` and returns the CUDA
+// status of the launch.  Element types are described by b200::DType.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "plan.h"
+
+namespace b200 {
+namespace kernels {
+
+// Every launcher bumps this process-wide counter (exported as B200KernelLaunchCount()).
+void CountLaunch(int n = 1);
+uint64_t LaunchCount();
+
+// A strided NHWC view: element (n,h,w,c) lives at base[((n*H + h)*W + w)*pitch + c_off + c].
+struct View {
+    void* base = nullptr;
+    DType dtype = DType::F32;
+    int C = 0, H = 1, W = 1;
+    int pitch = 0, c_off = 0;
+};
+
+struct ConvArgs {
+    View in, out;
+    int n = 0;  // batch
+    int R = 1, S = 1, stride = 1, pad = 0;
+    int Cin = 0, Cout = 0;
+    const float* pre_scale = nullptr;  // [Cin]  (x*scale+shift before the conv, only on in-bounds taps)
+    const float* pre_shift = nullptr;
+    bool pre_relu = false;
+    const float* bias = nullptr;  // [Cout]
+    bool post_relu = false;
+    bool pool2 = false;  // A rows are 2x2 averages of (prologue-transformed) input pixels
+};
+
+// ---- fp32 SIMT path ("FP32 reference mode"; also every rank-2 GEMM) ----
+// w_kn: fp32 [K = R*S*Cin][Cout]
+cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t stream);
+
+// ---- tcgen05 path (bf16 / e4m3 operands, fp32 accumulate in TMEM) ----
+struct UmmaWeights {
+    const void* w = nullptr;        // [Cout_pad][K_pad] in the MMA element type, K-major, zero padded
+    const float* out_scale = nullptr;  // [Cout] per-output-channel dequant scale (1.0 for bf16)
+    int K_pad = 0;                  // padded K (multiple of the 128-byte K chunk)
+    int Cout_pad = 0;
+    void* tensor_map = nullptr;     // device-visible CUtensorMap* (host memory, passed by value at launch)
+};
+cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
+// Host-side packing parameters for the tcgen05 path.
+int UmmaKChunkElems(DType mma_dtype);                       // elements per 128-byte K chunk
+int UmmaPaddedCin(int Cin, int R, int S, DType mma_dtype);  // per-tap channel padding used by the A loader
+bool UmmaSupported(const ConvArgs& a);
+
+// ---- memory-bound kernels (templated on element type inside) ----
+cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);
+cudaError_t NhwcToNchw(View in, float* out, int n, cudaStream_t stream);
+cudaError_t MaxPool(View in, View out, int n, int k, int stride, int pad, cudaStream_t stream);
+cudaError_t AvgPool(View in, View out, int n, int k, int stride, int pad, bool count_include_pad, cudaStream_t stream);
+cudaError_t BnRelu(View in, View out, int n, const float* scale, const float* shift, bool relu, cudaStream_t stream);
+cudaError_t GlobalAvgPool(View in, float* out, int out_pitch, int n, const float* scale, const float* shift, bool relu,
+                          cudaStream_t stream);
+cudaError_t AddTensors(View a, View b, View out, int n, cudaStream_t stream);
+cudaError_t CopyChannels(View in, View out, int n, cudaStream_t stream);
+cudaError_t ReluTensor(View in, View out, int n, cudaStream_t stream);
+cudaError_t SoftmaxRows(const float* in, float* out, int rows, int cols, cudaStream_t stream);
+cudaError_t FlushL2(void* scratch, size_t bytes, cudaStream_t stream);
+cudaError_t VectorAddF32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
+
+}  // namespace kernels
+}  // namespace b200

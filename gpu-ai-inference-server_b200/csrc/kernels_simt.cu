@@ -1,0 +1,546 @@
+// kernels_simt.cu — SIMT kernels of the engine (sm_100a):
+//   * conv_simt_f32: implicit-GEMM convolution in exact fp32 FFMA — the "FP32 reference mode" of the
+//     engine and the executor of every rank-2 Gemm/MatMul.  Fused A-operand prologue (folded
+//     BatchNormalization + ReLU, applied to in-bounds taps only) and bias/ReLU epilogue; reads and
+//     writes channel slices of wider NHWC pixels so dense-block concats never materialise.
+//   * the memory-bound kernels (layout conversion, pooling, BN+ReLU, global average pool, add, copy,
+//     softmax), templated on the storage type (f32 / bf16 / e4m3) with 128-bit vector accesses
+//     whenever the channel slice is 16-byte aligned.
+// These replace the cuDNN/cuBLAS library calls that ONNX Runtime's CUDA EP would make inside
+// `Ort::Session::Run` (reference inference_engine/src/model.cpp:1264-1270).
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+
+#include <atomic>
+#include <cfloat>
+
+#include "kernels.h"
+
+namespace b200 {
+namespace kernels {
+
+static std::atomic<uint64_t> g_launches{0};
+void CountLaunch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t LaunchCount() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+
+// ------------------------------------------------------------------ element helpers
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int V = 4;
+    __device__ static float ld(const float* p) { return *p; }
+    __device__ static void st(float* p, float v) { *p = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int V = 8;
+    __device__ static float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    __device__ static void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct Elem<__nv_fp8_e4m3> {
+    static constexpr int V = 16;
+    __device__ static float ld(const __nv_fp8_e4m3* p) { return float(*p); }
+    __device__ static void st(__nv_fp8_e4m3* p, float v) { *p = __nv_fp8_e4m3(v); }
+};
+
+template <typename T>
+__device__ __forceinline__ void LoadVec(const T* p, float* f) {
+    constexpr int V = Elem<T>::V;
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = Elem<T>::ld(e + i);
+}
+template <typename T>
+__device__ __forceinline__ void StoreVec(T* p, const float* f) {
+    constexpr int V = Elem<T>::V;
+    uint4 raw;
+    T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < V; ++i) Elem<T>::st(e + i, f[i]);
+    *reinterpret_cast<uint4*>(p) = raw;
+}
+
+template <typename T>
+bool VecOk(const View& v) {
+    constexpr int V = Elem<T>::V;
+    return v.C % V == 0 && v.pitch % V == 0 && v.c_off % V == 0 && (reinterpret_cast<uintptr_t>(v.base) % 16) == 0;
+}
+
+struct DView {  // device-side copy of View with typed access
+    void* base;
+    int C, H, W, pitch, c_off;
+};
+DView ToD(const View& v) { return DView{v.base, v.C, v.H, v.W, v.pitch, v.c_off}; }
+
+#define DISPATCH_DTYPE(dt, ...)                                              \
+    switch (dt) {                                                            \
+        case DType::F32: { using T = float; __VA_ARGS__; break; }            \
+        case DType::BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }   \
+        case DType::FP8: { using T = __nv_fp8_e4m3; __VA_ARGS__; break; }    \
+        default: return cudaErrorInvalidValue;                               \
+    }
+
+inline unsigned Blocks(size_t work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+// ------------------------------------------------------------------ layout conversion
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, DView out, int n) {
+    size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t hw = (size_t)out.H * out.W;
+    if (pix >= (size_t)n * hw) return;
+    size_t img = pix / hw, p = pix % hw;
+    T* o = reinterpret_cast<T*>(out.base) + pix * out.pitch + out.c_off;
+    for (int c = 0; c < out.C; ++c) Elem<T>::st(o + c, in[(img * out.C + c) * hw + p]);
+    // zero the channel padding so padded-K MMAs see exact zeros
+    if (out.c_off == 0)
+        for (int c = out.C; c < out.pitch; ++c) Elem<T>::st(o + c, 0.f);
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(DView in, float* __restrict__ out, int n) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t hw = (size_t)in.H * in.W;
+    size_t total = (size_t)n * in.C * hw;
+    if (idx >= total) return;
+    size_t p = idx % hw, c = (idx / hw) % in.C, img = idx / (hw * in.C);
+    const T* src = reinterpret_cast<const T*>(in.base) + (img * hw + p) * in.pitch + in.c_off + c;
+    out[idx] = Elem<T>::ld(src);
+}
+
+// ------------------------------------------------------------------ pooling
+template <typename T, bool VEC, bool IS_MAX>
+__global__ void pool_kernel(DView in, DView out, int n, int k, int stride, int pad, bool count_include_pad) {
+    constexpr int V = VEC ? Elem<T>::V : 1;
+    int cv = out.C / V;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)n * out.H * out.W * cv;
+    if (idx >= total) return;
+    int c = (int)(idx % cv) * V;
+    size_t opix = idx / cv;
+    int ow = (int)(opix % out.W);
+    int oh = (int)((opix / out.W) % out.H);
+    size_t img = opix / ((size_t)out.W * out.H);
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = IS_MAX ? -FLT_MAX : 0.f;
+    int cnt = 0;
+    for (int r = 0; r < k; ++r) {
+        int ih = oh * stride - pad + r;
+        if (ih < 0 || ih >= in.H) continue;
+        for (int s = 0; s < k; ++s) {
+            int iw = ow * stride - pad + s;
+            if (iw < 0 || iw >= in.W) continue;
+            const T* p = reinterpret_cast<const T*>(in.base) + ((img * in.H + ih) * in.W + iw) * in.pitch + in.c_off + c;
+            float v[V];
+            if (VEC) LoadVec<T>(p, v);
+            else v[0] = Elem<T>::ld(p);
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] = IS_MAX ? fmaxf(acc[i], v[i]) : acc[i] + v[i];
+            ++cnt;
+        }
+    }
+    if (!IS_MAX) {
+        float inv = 1.f / (float)(count_include_pad ? k * k : (cnt > 0 ? cnt : 1));
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] *= inv;
+    }
+    T* o = reinterpret_cast<T*>(out.base) + opix * out.pitch + out.c_off + c;
+    if (VEC) StoreVec<T>(o, acc);
+    else Elem<T>::st(o, acc[0]);
+}
+
+// ------------------------------------------------------------------ elementwise family
+// mode 0: y = relu?(x*scale+shift)   mode 1: y = a + b   mode 2: copy   mode 3: relu
+template <typename TI, typename TO, bool VEC, int MODE>
+__global__ void elementwise_kernel(DView a, DView b, DView out, size_t pixels, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, bool relu) {
+    constexpr int V = VEC ? (Elem<TI>::V < Elem<TO>::V ? Elem<TI>::V : Elem<TO>::V) : 1;
+    static_assert(!VEC || sizeof(TI) == sizeof(TO), "vector path needs equal element sizes");
+    int cv = out.C / V;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= pixels * cv) return;
+    int c = (int)(idx % cv) * V;
+    size_t pix = idx / cv;
+    const TI* pa = reinterpret_cast<const TI*>(a.base) + pix * a.pitch + a.c_off + c;
+    float x[V], y[V];
+    if (VEC) LoadVec<TI>(pa, x);
+    else x[0] = Elem<TI>::ld(pa);
+    if (MODE == 1) {
+        const TI* pb = reinterpret_cast<const TI*>(b.base) + pix * b.pitch + b.c_off + c;
+        if (VEC) LoadVec<TI>(pb, y);
+        else y[0] = Elem<TI>::ld(pb);
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        float v = x[i];
+        if (MODE == 0) {
+            v = fmaf(v, scale[c + i], shift[c + i]);
+            if (relu) v = fmaxf(v, 0.f);
+        } else if (MODE == 1) {
+            v += y[i];
+        } else if (MODE == 3) {
+            v = fmaxf(v, 0.f);
+        }
+        x[i] = v;
+    }
+    TO* po = reinterpret_cast<TO*>(out.base) + pix * out.pitch + out.c_off + c;
+    if (VEC) StoreVec<TO>(po, x);
+    else Elem<TO>::st(po, x[0]);
+}
+
+// ------------------------------------------------------------------ global average pool (+BN+ReLU)
+template <typename T, bool VEC>
+__global__ void gap_kernel(DView in, float* __restrict__ out, int out_pitch, int n, const float* __restrict__ scale,
+                           const float* __restrict__ shift, bool relu) {
+    constexpr int V = VEC ? Elem<T>::V : 1;
+    int cv = in.C / V;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * cv) return;
+    int c = (int)(idx % cv) * V;
+    size_t img = idx / cv;
+    int hw = in.H * in.W;
+    float sc[V], sh[V], acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        sc[i] = scale ? scale[c + i] : 1.f;
+        sh[i] = shift ? shift[c + i] : 0.f;
+        acc[i] = 0.f;
+    }
+    const T* p = reinterpret_cast<const T*>(in.base) + img * hw * (size_t)in.pitch + in.c_off + c;
+    for (int q = 0; q < hw; ++q, p += in.pitch) {
+        float v[V];
+        if (VEC) LoadVec<T>(p, v);
+        else v[0] = Elem<T>::ld(p);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float t = fmaf(v[i], sc[i], sh[i]);
+            acc[i] += relu ? fmaxf(t, 0.f) : t;
+        }
+    }
+    float inv = 1.f / (float)hw;
+#pragma unroll
+    for (int i = 0; i < V; ++i) out[img * out_pitch + c + i] = acc[i] * inv;
+}
+
+// ------------------------------------------------------------------ softmax over rows
+__global__ void softmax_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    int row = blockIdx.x;
+    if (row >= rows) return;
+    const float* x = in + (size_t)row * cols;
+    float* y = out + (size_t)row * cols;
+    __shared__ float red[32];
+    float m = -FLT_MAX;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, x[c]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) s += expf(x[c] - m);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    float inv = 1.f / s;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) y[c] = expf(x[c] - m) * inv;
+}
+
+__global__ void flush_kernel(uint4* p, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = make_uint4((unsigned)i, 0u, 0u, 0u);
+}
+
+__global__ void vector_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ r, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = a[i] + b[i];
+}
+
+// ------------------------------------------------------------------ fp32 implicit-GEMM convolution
+struct ConvP {
+    const float* in;
+    float* out;
+    const float* w;  // [K][Cout]
+    const float* bias;
+    const float* pre_scale;
+    const float* pre_shift;
+    int pre_relu, post_relu;
+    int H, W, Cin, in_pitch, in_coff;
+    int Ho, Wo, Cout, out_pitch, out_coff;
+    int R, S, stride, pad;
+    int M, K;
+    int vecA, vecB, vecC;
+};
+
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_simt_f32_kernel(ConvP p) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+        // ---- A tile: BM x BK gathered from NHWC input with prologue ----
+        if (p.vecA) {
+            constexpr int KQ = BK / 4;
+            for (int e = tid; e < BM * KQ; e += NT) {
+                int row = e / KQ, kq = (e % KQ) * 4;
+                int m = m0 + row, k = k0 + kq;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < p.M && k < p.K) {
+                    int c = k % p.Cin, rs = k / p.Cin;
+                    int s = rs % p.S, r = rs / p.S;
+                    int ow = m % p.Wo, oh = (m / p.Wo) % p.Ho, img = m / (p.Wo * p.Ho);
+                    int ih = oh * p.stride - p.pad + r, iw = ow * p.stride - p.pad + s;
+                    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                        const float* src = p.in + ((size_t)(img * p.H + ih) * p.W + iw) * p.in_pitch + p.in_coff + c;
+                        v = *reinterpret_cast<const float4*>(src);
+                        if (p.pre_scale) {
+                            float4 sc = *reinterpret_cast<const float4*>(p.pre_scale + c);
+                            float4 sh = *reinterpret_cast<const float4*>(p.pre_shift + c);
+                            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                            v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        }
+                        if (p.pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    }
+                }
+                As[kq + 0][row] = v.x; As[kq + 1][row] = v.y; As[kq + 2][row] = v.z; As[kq + 3][row] = v.w;
+            }
+        } else {
+            for (int e = tid; e < BM * BK; e += NT) {
+                int row = e / BK, kk = e % BK;
+                int m = m0 + row, k = k0 + kk;
+                float v = 0.f;
+                if (m < p.M && k < p.K) {
+                    int c = k % p.Cin, rs = k / p.Cin;
+                    int s = rs % p.S, r = rs / p.S;
+                    int ow = m % p.Wo, oh = (m / p.Wo) % p.Ho, img = m / (p.Wo * p.Ho);
+                    int ih = oh * p.stride - p.pad + r, iw = ow * p.stride - p.pad + s;
+                    if (ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                        v = p.in[((size_t)(img * p.H + ih) * p.W + iw) * p.in_pitch + p.in_coff + c];
+                        if (p.pre_scale) v = fmaf(v, p.pre_scale[c], p.pre_shift[c]);
+                        if (p.pre_relu) v = fmaxf(v, 0.f);
+                    }
+                }
+                As[kk][row] = v;
+            }
+        }
+        // ---- B tile: BK x BN of w[K][Cout] ----
+        if (p.vecB) {
+            constexpr int NQ = BN / 4;
+            for (int e = tid; e < BK * NQ; e += NT) {
+                int kk = e / NQ, nq = (e % NQ) * 4;
+                int k = k0 + kk, nn = n0 + nq;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < p.K && nn < p.Cout) v = *reinterpret_cast<const float4*>(p.w + (size_t)k * p.Cout + nn);
+                *reinterpret_cast<float4*>(&Bs[kk][nq]) = v;
+            }
+        } else {
+            for (int e = tid; e < BK * BN; e += NT) {
+                int kk = e / BN, nq = e % BN;
+                int k = k0 + kk, nn = n0 + nq;
+                Bs[kk][nq] = (k < p.K && nn < p.Cout) ? p.w[(size_t)k * p.Cout + nn] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; i += 4) {
+                float4 t = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+                a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                float4 t = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + j]);
+                b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue ----
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int m = m0 + ty * TM + i;
+        if (m >= p.M) continue;
+        float* orow = p.out + (size_t)m * p.out_pitch + p.out_coff;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            int nn = n0 + tx * TN + j;
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float t = acc[i][j + q];
+                if (p.bias && nn + q < p.Cout) t += p.bias[nn + q];
+                if (p.post_relu) t = fmaxf(t, 0.f);
+                v[q] = t;
+            }
+            if (p.vecC && nn + 3 < p.Cout) {
+                *reinterpret_cast<float4*>(orow + nn) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (nn + q < p.Cout) orow[nn + q] = v[q];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ====================================================================== launchers
+cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t stream) {
+    if (a.in.dtype != DType::F32 || a.out.dtype != DType::F32 || a.pool2) return cudaErrorInvalidValue;
+    ConvP p;
+    p.in = (const float*)a.in.base; p.out = (float*)a.out.base; p.w = w_kn; p.bias = a.bias;
+    p.pre_scale = a.pre_scale; p.pre_shift = a.pre_shift; p.pre_relu = a.pre_relu; p.post_relu = a.post_relu;
+    p.H = a.in.H; p.W = a.in.W; p.Cin = a.Cin; p.in_pitch = a.in.pitch; p.in_coff = a.in.c_off;
+    p.Ho = a.out.H; p.Wo = a.out.W; p.Cout = a.Cout; p.out_pitch = a.out.pitch; p.out_coff = a.out.c_off;
+    p.R = a.R; p.S = a.S; p.stride = a.stride; p.pad = a.pad;
+    p.M = a.n * p.Ho * p.Wo; p.K = a.R * a.S * a.Cin;
+    p.vecA = (a.Cin % 4 == 0 && a.in.pitch % 4 == 0 && a.in.c_off % 4 == 0 && ((uintptr_t)p.in % 16) == 0 &&
+              (!a.pre_scale || (((uintptr_t)a.pre_scale % 16) == 0 && ((uintptr_t)a.pre_shift % 16) == 0)));
+    p.vecB = (a.Cout % 4 == 0 && ((uintptr_t)w_kn % 16) == 0);
+    p.vecC = (a.out.pitch % 4 == 0 && a.out.c_off % 4 == 0 && ((uintptr_t)p.out % 16) == 0);
+    if (p.M <= 0) return cudaSuccess;
+    if (a.Cout <= 32) {
+        constexpr int BM = 128, BN = 32;
+        dim3 grid((p.M + BM - 1) / BM, (a.Cout + BN - 1) / BN);
+        conv_simt_f32_kernel<BM, BN, 16, 4, 4><<<grid, 256, 0, stream>>>(p);
+    } else {
+        constexpr int BM = 128, BN = 64;
+        dim3 grid((p.M + BM - 1) / BM, (a.Cout + BN - 1) / BN);
+        conv_simt_f32_kernel<BM, BN, 16, 8, 4><<<grid, 256, 0, stream>>>(p);
+    }
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream) {
+    size_t pixels = (size_t)n * out.H * out.W;
+    if (!pixels) return cudaSuccess;
+    DISPATCH_DTYPE(out.dtype, (nchw_to_nhwc_kernel<T><<<Blocks(pixels, 256), 256, 0, stream>>>(in, ToD(out), n)));
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+cudaError_t NhwcToNchw(View in, float* out, int n, cudaStream_t stream) {
+    size_t total = (size_t)n * in.C * in.H * in.W;
+    if (!total) return cudaSuccess;
+    DISPATCH_DTYPE(in.dtype, (nhwc_to_nchw_kernel<T><<<Blocks(total, 256), 256, 0, stream>>>(ToD(in), out, n)));
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+template <bool IS_MAX>
+static cudaError_t PoolImpl(View in, View out, int n, int k, int stride, int pad, bool cip, cudaStream_t stream) {
+    if (in.dtype != out.dtype || in.C != out.C) return cudaErrorInvalidValue;
+    size_t opix = (size_t)n * out.H * out.W;
+    if (!opix) return cudaSuccess;
+    DISPATCH_DTYPE(in.dtype, {
+        if (VecOk<T>(in) && VecOk<T>(out))
+            pool_kernel<T, true, IS_MAX><<<Blocks(opix * (out.C / Elem<T>::V), 256), 256, 0, stream>>>(ToD(in), ToD(out), n, k, stride, pad, cip);
+        else
+            pool_kernel<T, false, IS_MAX><<<Blocks(opix * out.C, 256), 256, 0, stream>>>(ToD(in), ToD(out), n, k, stride, pad, cip);
+    });
+    CountLaunch();
+    return cudaGetLastError();
+}
+cudaError_t MaxPool(View in, View out, int n, int k, int stride, int pad, cudaStream_t stream) {
+    return PoolImpl<true>(in, out, n, k, stride, pad, false, stream);
+}
+cudaError_t AvgPool(View in, View out, int n, int k, int stride, int pad, bool count_include_pad, cudaStream_t stream) {
+    return PoolImpl<false>(in, out, n, k, stride, pad, count_include_pad, stream);
+}
+
+template <int MODE>
+static cudaError_t ElementwiseImpl(View a, View b, View out, int n, const float* scale, const float* shift, bool relu,
+                                   cudaStream_t stream) {
+    if (a.C != out.C || a.H != out.H || a.W != out.W) return cudaErrorInvalidValue;
+    size_t pixels = (size_t)n * out.H * out.W;
+    if (!pixels) return cudaSuccess;
+    if (a.dtype == out.dtype) {
+        DISPATCH_DTYPE(a.dtype, {
+            bool vec = VecOk<T>(a) && VecOk<T>(out) && (MODE != 1 || VecOk<T>(b));
+            if (vec)
+                elementwise_kernel<T, T, true, MODE><<<Blocks(pixels * (out.C / Elem<T>::V), 256), 256, 0, stream>>>(
+                    ToD(a), ToD(b), ToD(out), pixels, scale, shift, relu);
+            else
+                elementwise_kernel<T, T, false, MODE><<<Blocks(pixels * out.C, 256), 256, 0, stream>>>(
+                    ToD(a), ToD(b), ToD(out), pixels, scale, shift, relu);
+        });
+    } else if (out.dtype == DType::F32) {
+        DISPATCH_DTYPE(a.dtype, (elementwise_kernel<T, float, false, MODE><<<Blocks(pixels * out.C, 256), 256, 0, stream>>>(
+                                    ToD(a), ToD(b), ToD(out), pixels, scale, shift, relu)));
+    } else {
+        return cudaErrorInvalidValue;
+    }
+    CountLaunch();
+    return cudaGetLastError();
+}
+cudaError_t BnRelu(View in, View out, int n, const float* scale, const float* shift, bool relu, cudaStream_t stream) {
+    return ElementwiseImpl<0>(in, in, out, n, scale, shift, relu, stream);
+}
+cudaError_t AddTensors(View a, View b, View out, int n, cudaStream_t stream) {
+    if (a.dtype != b.dtype) return cudaErrorInvalidValue;
+    return ElementwiseImpl<1>(a, b, out, n, nullptr, nullptr, false, stream);
+}
+cudaError_t CopyChannels(View in, View out, int n, cudaStream_t stream) {
+    return ElementwiseImpl<2>(in, in, out, n, nullptr, nullptr, false, stream);
+}
+cudaError_t ReluTensor(View in, View out, int n, cudaStream_t stream) {
+    return ElementwiseImpl<3>(in, in, out, n, nullptr, nullptr, false, stream);
+}
+
+cudaError_t GlobalAvgPool(View in, float* out, int out_pitch, int n, const float* scale, const float* shift, bool relu,
+                          cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    DISPATCH_DTYPE(in.dtype, {
+        if (VecOk<T>(in))
+            gap_kernel<T, true><<<Blocks((size_t)n * (in.C / Elem<T>::V), 128), 128, 0, stream>>>(ToD(in), out, out_pitch, n, scale, shift, relu);
+        else
+            gap_kernel<T, false><<<Blocks((size_t)n * in.C, 128), 128, 0, stream>>>(ToD(in), out, out_pitch, n, scale, shift, relu);
+    });
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+cudaError_t SoftmaxRows(const float* in, float* out, int rows, int cols, cudaStream_t stream) {
+    if (!rows) return cudaSuccess;
+    softmax_kernel<<<rows, 256, 0, stream>>>(in, out, rows, cols);
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+cudaError_t FlushL2(void* scratch, size_t bytes, cudaStream_t stream) {
+    flush_kernel<<<148 * 8, 256, 0, stream>>>((uint4*)scratch, bytes / 16);
+    return cudaGetLastError();
+}
+
+cudaError_t VectorAddF32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream) {
+    if (!n) return cudaSuccess;
+    vector_add_kernel<<<Blocks(n, 256), 256, 0, stream>>>(a, b, out, n);
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+}  // namespace kernels
+}  // namespace b200

@@ -1,0 +1,534 @@
+// model.cpp — inference::Tensor, inference::Model and ModelImpl.
+//
+// Mirrors the control flow of reference `inference_engine/src/model.cpp`:
+//   Load   : file checks + per-type dispatch (:503-548)  -> here: ONNX import + plan + per-GPU replicas
+//   Infer  : loaded check, ValidateInputs (:734-794), dispatch, wall-clock stats (:557-613)
+//   InferONNX (:1158-1328): inputs looked up BY NAME, outputs returned in graph order, fp32 only
+// What differs on purpose (INTEGRATION.md "deviations"): I/O names come from the ONNX graph when the
+// configured names do not occur in it (fixes SURVEY.md 0.7), any leading batch dimension is accepted,
+// stats are atomics, and nothing executes on the CPU.
+#include "model.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <future>
+#include <sstream>
+#include <sys/stat.h>
+
+#include "cuda_utils.h"
+#include "json_lite.h"
+#include "model_impl.h"
+#include "onnx_wire.h"
+
+namespace inference {
+
+// ============================================================================ Tensor
+class Tensor::TensorImpl {
+public:
+    std::string name;
+    DataType dtype = DataType::FLOAT32;
+    Shape shape;
+    std::vector<uint8_t> host;
+    void* dev = nullptr;
+    int device_id = 0;
+
+    static size_t ElemSize(DataType t) {
+        switch (t) {
+            case DataType::FLOAT32: case DataType::INT32: return 4;
+            case DataType::INT64: return 8;
+            case DataType::FP16: return 2;
+            case DataType::UINT8: case DataType::INT8: case DataType::BOOL: return 1;
+            default: return 0;  // STRING / UNKNOWN carry no fixed-size payload
+        }
+    }
+    size_t Bytes() const { return shape.NumElements() * ElemSize(dtype); }
+    void DropDevice() {
+        if (dev) {
+            cudaSetDevice(device_id);
+            cudaFree(dev);
+            dev = nullptr;
+        }
+    }
+    ~TensorImpl() { DropDevice(); }
+};
+
+Tensor::Tensor() : impl_(new TensorImpl()) {}
+Tensor::Tensor(const std::string& name, DataType dtype, const Shape& shape) : impl_(new TensorImpl()) {
+    impl_->name = name;
+    impl_->dtype = dtype;
+    impl_->shape = shape;
+    impl_->host.resize(impl_->Bytes());
+}
+Tensor::Tensor(const Tensor& o) : impl_(new TensorImpl()) {
+    // deep copy of the host payload; a device mirror is never shared (the reference aliased it, model.cpp:205)
+    impl_->name = o.impl_->name;
+    impl_->dtype = o.impl_->dtype;
+    impl_->shape = o.impl_->shape;
+    impl_->host = o.impl_->host;
+}
+Tensor::Tensor(Tensor&& o) noexcept : impl_(std::move(o.impl_)) { o.impl_.reset(new TensorImpl()); }
+Tensor& Tensor::operator=(const Tensor& o) {
+    if (this != &o) {
+        impl_->DropDevice();
+        impl_->name = o.impl_->name;
+        impl_->dtype = o.impl_->dtype;
+        impl_->shape = o.impl_->shape;
+        impl_->host = o.impl_->host;
+    }
+    return *this;
+}
+Tensor::~Tensor() = default;
+
+const std::string& Tensor::GetName() const { return impl_->name; }
+DataType Tensor::GetDataType() const { return impl_->dtype; }
+const Shape& Tensor::GetShape() const { return impl_->shape; }
+const void* Tensor::RawData() const { return impl_->host.data(); }
+void* Tensor::MutableRawData() { return impl_->host.data(); }
+size_t Tensor::ByteSize() const { return impl_->host.size(); }
+
+bool Tensor::Reshape(const Shape& new_shape) {
+    size_t before = impl_->shape.NumElements();
+    impl_->shape = new_shape;  // (the reference forgot this when the element count is unchanged, model.cpp:278-305)
+    if (impl_->shape.NumElements() != before) {
+        impl_->host.resize(impl_->Bytes());
+        impl_->DropDevice();
+    }
+    return true;
+}
+
+bool Tensor::toGPU(int device_id) {
+    if (!cuda::IsCudaAvailable()) return false;
+    if (impl_->dev) return true;
+    if (cudaSetDevice(device_id) != cudaSuccess) return false;
+    impl_->device_id = device_id;
+    if (cudaMalloc(&impl_->dev, std::max<size_t>(impl_->Bytes(), 1)) != cudaSuccess) { impl_->dev = nullptr; return false; }
+    if (cudaMemcpy(impl_->dev, impl_->host.data(), impl_->Bytes(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        impl_->DropDevice();
+        return false;
+    }
+    return true;
+}
+bool Tensor::toCPU() {
+    if (!impl_->dev) return true;
+    if (cudaSetDevice(impl_->device_id) != cudaSuccess) return false;
+    if (cudaMemcpy(impl_->host.data(), impl_->dev, impl_->Bytes(), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    impl_->DropDevice();
+    return true;
+}
+
+namespace {
+template <typename T>
+bool SetTyped(std::vector<uint8_t>& host, const Shape& shape, DataType have, DataType want, const std::vector<T>& data) {
+    if (have != want || data.size() != shape.NumElements()) return false;  // reference model.cpp:96-106
+    host.resize(data.size() * sizeof(T));
+    if (!data.empty()) memcpy(host.data(), data.data(), host.size());
+    return true;
+}
+template <typename T>
+bool GetTyped(const std::vector<uint8_t>& host, const Shape& shape, DataType have, DataType want, std::vector<T>& data) {
+    if (have != want) return false;
+    data.resize(shape.NumElements());
+    if (!data.empty()) memcpy(data.data(), host.data(), std::min(host.size(), data.size() * sizeof(T)));
+    return true;
+}
+}  // namespace
+
+template <> bool Tensor::SetData(const std::vector<float>& d) { return SetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::FLOAT32, d); }
+template <> bool Tensor::GetData(std::vector<float>& d) const { return GetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::FLOAT32, d); }
+template <> bool Tensor::SetData(const std::vector<int>& d) { return SetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::INT32, d); }
+template <> bool Tensor::GetData(std::vector<int>& d) const { return GetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::INT32, d); }
+template <> bool Tensor::SetData(const std::vector<long>& d) { return SetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::INT64, d); }
+template <> bool Tensor::GetData(std::vector<long>& d) const { return GetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::INT64, d); }
+template <> bool Tensor::SetData(const std::vector<uint8_t>& d) { return SetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::UINT8, d); }
+template <> bool Tensor::GetData(std::vector<uint8_t>& d) const { return GetTyped(impl_->host, impl_->shape, impl_->dtype, DataType::UINT8, d); }
+
+// ============================================================================ ModelImpl
+namespace {
+
+bool PathExists(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+
+std::string EnvOr(const char* name, const std::string& dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? std::string(v) : dflt;
+}
+
+std::vector<int> ParseDeviceList(const std::string& spec, int device_count, int default_device) {
+    std::vector<int> out;
+    if (spec.empty() || spec == "all") {
+        for (int i = 0; i < device_count; ++i) out.push_back(i);
+        return out;
+    }
+    if (spec == "default") return {default_device};
+    std::stringstream ss(spec);
+    std::string tok;
+    while (std::getline(ss, tok, ',')) {
+        if (tok.empty()) continue;
+        int d = atoi(tok.c_str());
+        if (d < 0 || d >= device_count) throw std::runtime_error("B200_ENGINE_DEVICES names device " + tok + " but only " + std::to_string(device_count) + " are visible");
+        out.push_back(d);
+    }
+    if (out.empty()) out.push_back(default_device);
+    return out;
+}
+
+}  // namespace
+
+ModelImpl::ModelImpl(const std::string& model_path, ModelType type, const ModelConfig& config, DeviceType device, int device_id)
+    : model_path_(model_path), type_(type), config_(config), device_type_(device), device_id_(device_id) {
+    metadata_.name = config_.name;
+    metadata_.version = config_.version;
+    metadata_.type = type_;
+    metadata_.inputs = config_.input_names;
+    metadata_.outputs = config_.output_names;
+    metadata_.load_time_ns = 0;
+}
+
+ModelImpl::~ModelImpl() { Unload(); }
+
+std::string ModelImpl::GetLastError() const {
+    std::lock_guard<std::mutex> lk(err_mu_);
+    return last_error_;
+}
+void ModelImpl::SetLastError(const std::string& e) const {
+    std::lock_guard<std::mutex> lk(err_mu_);
+    last_error_ = e;
+}
+ModelMetadata ModelImpl::GetMetadata() const {
+    std::lock_guard<std::mutex> lk(state_mu_);
+    return metadata_;
+}
+Model::Stats ModelImpl::GetStats() const {
+    Model::Stats s;
+    s.inference_count = inference_count_.load();
+    s.total_inference_time_ns = total_ns_.load();
+    s.last_inference_time_ns = last_ns_.load();
+    s.memory_usage_bytes = memory_bytes_.load();
+    return s;
+}
+std::shared_ptr<ModelImpl::Loaded> ModelImpl::Pin() const {
+    std::lock_guard<std::mutex> lk(state_mu_);
+    return state_;
+}
+
+bool ModelImpl::Load() {
+    auto t0 = std::chrono::high_resolution_clock::now();
+    if (IsLoaded()) return true;
+    if (!PathExists(model_path_)) {
+        SetLastError("Model file not found: " + model_path_);
+        return false;
+    }
+    switch (type_) {
+        case ModelType::ONNX: break;
+        case ModelType::TENSORFLOW: SetLastError("TensorFlow model loading not implemented"); return false;
+        case ModelType::TENSORRT: SetLastError("TensorRT model loading not implemented"); return false;
+        case ModelType::PYTORCH: SetLastError("PyTorch model loading not implemented"); return false;
+        case ModelType::CUSTOM: SetLastError("Custom model loading not implemented"); return false;
+        default: SetLastError("Unsupported model type"); return false;
+    }
+    const std::string onnx_path = model_path_ + "/model.onnx";
+    if (!PathExists(onnx_path)) {
+        SetLastError("ONNX model file not found: " + onnx_path);
+        return false;
+    }
+    try {
+        if (device_type_ != DeviceType::GPU)
+            throw std::runtime_error("this engine executes on NVIDIA B200 (sm_100a) only; DeviceType::CPU is not available");
+        int ndev = cuda::GetDeviceCount();
+        if (ndev <= 0) throw std::runtime_error("no CUDA device is visible; this engine has no CPU execution path");
+
+        // optional per-model settings (config.json next to model.onnx), environment wins
+        std::string precision_s = "fp32";
+        int max_batch = config_.max_batch_size > 0 ? config_.max_batch_size : 256;
+        {
+            std::ifstream cf(model_path_ + "/config.json");
+            if (cf) {
+                std::stringstream ss;
+                ss << cf.rdbuf();
+                try {
+                    b200::json::Value v = b200::json::ParseString(ss.str());
+                    if (auto* p = v.Get("precision")) if (p->kind == b200::json::Value::String) precision_s = p->str;
+                    if (auto* p = v.Get("max_batch_size")) if (p->kind == b200::json::Value::Number && p->num >= 1) max_batch = (int)p->num;
+                } catch (...) { /* a malformed config.json never blocks loading (the reference ignores it) */ }
+            }
+        }
+        precision_s = EnvOr("B200_ENGINE_PRECISION", precision_s);
+        max_batch = atoi(EnvOr("B200_ENGINE_MAX_BATCH", std::to_string(max_batch)).c_str());
+        if (max_batch < 1) max_batch = 1;
+        b200::Precision precision;
+        if (!b200::ParsePrecision(precision_s, &precision)) throw std::runtime_error("unknown precision '" + precision_s + "' (use fp32, bf16 or fp8)");
+
+        b200::onnx::Model om = b200::onnx::ParseFile(onnx_path);
+        auto plan = std::make_shared<b200::Plan>(b200::BuildPlan(om, precision, max_batch));
+
+        std::vector<int> devices = ParseDeviceList(EnvOr("B200_ENGINE_DEVICES", "all"), ndev, device_id_);
+        bool graphs = EnvOr("B200_ENGINE_GRAPHS", "1") != "0";
+        auto st = std::make_shared<Loaded>();
+        st->plan = plan;
+        size_t mem = 0;
+        for (int d : devices) {
+            st->replicas.emplace_back(new b200::Replica(d, plan, graphs));
+            mem += st->replicas.back()->DeviceBytes();
+        }
+        memory_bytes_.store(mem);
+
+        {
+            std::lock_guard<std::mutex> lk(state_mu_);
+            // Names: keep the configured ones when they exist in the graph, else adopt the graph's
+            // (reference defaults to "input"/"output", model_repository.cpp:143-144, which rejects DenseNet).
+            auto all_in = [&](const std::vector<std::string>& want, const std::vector<std::string>& have) {
+                if (want.size() != have.size()) return false;
+                for (auto& w : want) if (std::find(have.begin(), have.end(), w) == have.end()) return false;
+                return true;
+            };
+            if (!all_in(config_.input_names, plan->input_names)) config_.input_names = plan->input_names;
+            if (!all_in(config_.output_names, plan->output_names)) config_.output_names = plan->output_names;
+            for (size_t i = 0; i < plan->input_names.size(); ++i) {
+                Shape s;
+                s.dims = plan->input_dims[i];  // -1 batch wildcard
+                config_.input_shapes[plan->input_names[i]] = s;
+                config_.input_types[plan->input_names[i]] = DataType::FLOAT32;
+            }
+            for (size_t i = 0; i < plan->output_names.size(); ++i) {
+                Shape s;
+                s.dims = plan->output_dims[i];
+                config_.output_shapes[plan->output_names[i]] = s;
+                config_.output_types[plan->output_names[i]] = DataType::FLOAT32;
+            }
+            metadata_.inputs = config_.input_names;
+            metadata_.outputs = config_.output_names;
+            metadata_.description = std::string("b200-engine ") + b200::PrecisionName(precision) + " plan: " +
+                                    std::to_string(plan->steps.size()) + " steps, " + std::to_string(devices.size()) + " GPU replica(s)";
+            state_ = st;
+        }
+        loaded_.store(true, std::memory_order_release);
+    } catch (const std::exception& e) {
+        SetLastError(std::string("ONNX model loading error: ") + e.what());
+        return false;
+    }
+    auto t1 = std::chrono::high_resolution_clock::now();
+    {
+        std::lock_guard<std::mutex> lk(state_mu_);
+        metadata_.load_time_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+    }
+    return true;
+}
+
+void ModelImpl::Unload() {
+    std::shared_ptr<Loaded> old;
+    {
+        std::lock_guard<std::mutex> lk(state_mu_);
+        old.swap(state_);
+    }
+    loaded_.store(false, std::memory_order_release);
+    memory_bytes_.store(0);
+    // `old` (replicas, arenas) is released here unless an in-flight Infer still pins it.
+}
+
+bool ModelImpl::ValidateInputs(const std::vector<IoDesc>& ins) const {
+    // reference model.cpp:734-794, same messages
+    if (ins.size() != config_.input_names.size()) {
+        SetLastError("Expected " + std::to_string(config_.input_names.size()) + " inputs, got " + std::to_string(ins.size()));
+        return false;
+    }
+    for (const auto& in : ins) {
+        if (std::find(config_.input_names.begin(), config_.input_names.end(), in.name) == config_.input_names.end()) {
+            SetLastError("Unexpected input name: " + in.name);
+            return false;
+        }
+        auto ti = config_.input_types.find(in.name);
+        if (ti != config_.input_types.end() && ti->second != in.dtype) {
+            SetLastError("Input data type mismatch for " + in.name);
+            return false;
+        }
+        auto si = config_.input_shapes.find(in.name);
+        if (si != config_.input_shapes.end()) {
+            const auto& want = si->second.dims;
+            if (want.size() != in.dims.size()) {
+                SetLastError("Input shape mismatch for " + in.name + ": expected " + std::to_string(want.size()) +
+                             " dimensions, got " + std::to_string(in.dims.size()));
+                return false;
+            }
+            for (size_t i = 0; i < want.size(); ++i)
+                if (want[i] != -1 && want[i] != in.dims[i]) {
+                    SetLastError("Input shape mismatch for " + in.name + " at dimension " + std::to_string(i));
+                    return false;
+                }
+        }
+    }
+    return true;
+}
+
+bool ModelImpl::Infer(const std::vector<Tensor>& inputs, std::vector<Tensor>& outputs) {
+    std::vector<IoDesc> ins(inputs.size());
+    for (size_t i = 0; i < inputs.size(); ++i) {
+        ins[i].name = inputs[i].GetName();
+        ins[i].dtype = inputs[i].GetDataType();
+        ins[i].dims = inputs[i].GetShape().dims;
+        ins[i].data = inputs[i].RawData();
+        ins[i].bytes = inputs[i].ByteSize();
+    }
+    auto st = Pin();
+    if (!IsLoaded() || !st) {
+        SetLastError("Model not loaded");
+        return false;
+    }
+    // Output tensors are created by the engine in graph order (reference model.cpp:1273-1314 clears and refills).
+    int64_t n = (!ins.empty() && !ins[0].dims.empty()) ? ins[0].dims[0] : 0;
+    outputs.clear();
+    std::vector<OutDesc> outs(st->plan->outputs.size());
+    if (n > 0) {
+        for (size_t i = 0; i < outs.size(); ++i) {
+            Shape s;
+            s.dims = st->plan->output_dims[i];
+            s.dims[0] = n;
+            outputs.emplace_back(st->plan->output_names[i], DataType::FLOAT32, s);
+        }
+        for (size_t i = 0; i < outs.size(); ++i) {
+            outs[i].data = outputs[i].MutableRawData();
+            outs[i].capacity = outputs[i].ByteSize();
+        }
+    }
+    bool ok = InferBorrowed(ins, outs);
+    if (!ok) outputs.clear();
+    return ok;
+}
+
+bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDesc>& outs) {
+    auto st = Pin();
+    if (!IsLoaded() || !st) {
+        SetLastError("Model not loaded");
+        return false;
+    }
+    if (!ValidateInputs(ins)) return false;
+    auto t0 = std::chrono::high_resolution_clock::now();
+    bool ok = false;
+    try {
+        const b200::Plan& P = *st->plan;
+        // by-name binding of graph inputs (reference model.cpp:1173-1222)
+        std::vector<const void*> ptrs(P.input_names.size(), nullptr);
+        int64_t n = -1;
+        for (size_t gi = 0; gi < P.input_names.size(); ++gi) {
+            const IoDesc* found = nullptr;
+            for (const auto& in : ins) if (in.name == P.input_names[gi]) { found = &in; break; }
+            if (!found) throw std::runtime_error("Required input tensor not provided: " + P.input_names[gi]);
+            if (found->dtype != DataType::FLOAT32) throw std::runtime_error("Unsupported data type for input: " + found->name);
+            const auto& gd = P.input_dims[gi];
+            if (found->dims.size() != gd.size() || found->dims.empty() || found->dims[0] < 1)
+                throw std::runtime_error("Invalid FLOAT32 data for input: " + found->name);
+            size_t per = 1;
+            for (size_t k = 1; k < gd.size(); ++k) {
+                if (found->dims[k] != gd[k]) throw std::runtime_error("Input shape mismatch for " + found->name + " at dimension " + std::to_string(k));
+                per *= (size_t)gd[k];
+            }
+            if (n < 0) n = found->dims[0];
+            else if (n != found->dims[0]) throw std::runtime_error("Inputs disagree on the batch dimension");
+            if (!found->data || found->bytes < (size_t)n * per * 4) throw std::runtime_error("Invalid FLOAT32 data for input: " + found->name);
+            ptrs[gi] = found->data;
+        }
+        ok = Execute(*st, (int)n, ptrs, outs);
+    } catch (const std::exception& e) {
+        SetLastError(std::string("ONNX inference error: ") + e.what());
+        ok = false;
+    }
+    auto t1 = std::chrono::high_resolution_clock::now();
+    int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+    inference_count_.fetch_add(1);
+    total_ns_.fetch_add(ns);
+    last_ns_.store(ns);
+    return ok;
+}
+
+// The multi-GPU batch scheduler: contiguous split of the batch over replicas, no collective
+// (SURVEY.md §8e).  Small batches go to one replica chosen round-robin so concurrent callers spread.
+bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs) {
+    const b200::Plan& P = *st.plan;
+    const int G = (int)st.replicas.size();
+    const int max_b = P.max_batch;
+    std::vector<size_t> in_stride(P.inputs.size()), out_stride(P.outputs.size());
+    for (size_t i = 0; i < P.inputs.size(); ++i) {
+        const auto& t = P.tensors[P.inputs[i]];
+        in_stride[i] = (size_t)t.C * t.H * t.W * 4;
+    }
+    for (size_t i = 0; i < P.outputs.size(); ++i) {
+        const auto& t = P.tensors[P.outputs[i]];
+        out_stride[i] = (size_t)t.C * t.H * t.W * 4;
+    }
+    for (size_t i = 0; i < outs.size(); ++i) {
+        if (i >= P.outputs.size()) break;
+        outs[i].name = P.output_names[i];
+        outs[i].dims = P.output_dims[i];
+        outs[i].dims[0] = n;
+        outs[i].produced = (size_t)n * out_stride[i];
+    }
+    static const int kMinShard = std::max(1, atoi(EnvOr("B200_ENGINE_MIN_SHARD", "8").c_str()));
+    struct Shard { int replica, off, cnt; };
+    std::vector<Shard> shards;
+    int use = std::min(G, std::max(1, n / kMinShard));
+    if (use <= 1) {
+        int r = (int)(round_robin_.fetch_add(1) % (unsigned)G);
+        for (int off = 0; off < n; off += max_b) shards.push_back({r, off, std::min(max_b, n - off)});
+    } else {
+        int base = n / use, rem = n % use, off = 0;
+        for (int g = 0; g < use; ++g) {
+            int cnt = base + (g < rem ? 1 : 0);
+            for (int o = 0; o < cnt; o += max_b) shards.push_back({g, off + o, std::min(max_b, cnt - o)});
+            off += cnt;
+        }
+    }
+    auto run_shard = [&](const Shard& s) {
+        std::vector<const void*> ip(P.inputs.size());
+        std::vector<void*> op(outs.size(), nullptr);
+        std::vector<size_t> cap(outs.size(), 0);
+        for (size_t i = 0; i < ip.size(); ++i) ip[i] = (const char*)in_ptrs[i] + (size_t)s.off * in_stride[i];
+        for (size_t i = 0; i < outs.size() && i < P.outputs.size(); ++i) {
+            size_t begin = (size_t)s.off * out_stride[i];
+            if (!outs[i].data || begin >= outs[i].capacity) continue;
+            op[i] = (char*)outs[i].data + begin;
+            cap[i] = outs[i].capacity - begin;
+        }
+        st.replicas[s.replica]->Run(s.cnt, ip, op, cap);
+    };
+    if (use <= 1) {
+        for (auto& s : shards) run_shard(s);
+        return true;
+    }
+    // one host thread per participating replica; shards of the same replica run back to back on it
+    std::vector<std::future<void>> futs;
+    for (int g = 1; g < use; ++g)
+        futs.push_back(std::async(std::launch::async, [&, g] {
+            for (auto& s : shards) if (s.replica == g) run_shard(s);
+        }));
+    std::exception_ptr first;
+    try {
+        for (auto& s : shards) if (s.replica == 0) run_shard(s);
+    } catch (...) { first = std::current_exception(); }
+    for (auto& f : futs) {
+        try { f.get(); } catch (...) { if (!first) first = std::current_exception(); }
+    }
+    if (first) std::rethrow_exception(first);
+    return true;
+}
+
+// ============================================================================ Model (thin PIMPL shell)
+Model::Model(const std::string& model_path, ModelType type, const ModelConfig& config, DeviceType device, int device_id)
+    : impl_(new ModelImpl(model_path, type, config, device, device_id)) {}
+Model::~Model() = default;
+Model::Model(Model&&) noexcept = default;
+Model& Model::operator=(Model&&) noexcept = default;
+bool Model::Load() { return impl_->Load(); }
+bool Model::Infer(const std::vector<Tensor>& inputs, std::vector<Tensor>& outputs) { return impl_->Infer(inputs, outputs); }
+ModelMetadata Model::GetMetadata() const { return impl_->GetMetadata(); }
+bool Model::IsLoaded() const { return impl_->IsLoaded(); }
+void Model::Unload() { impl_->Unload(); }
+std::string Model::GetLastError() const { return impl_->GetLastError(); }
+Model::Stats Model::GetStats() const { return impl_->GetStats(); }
+
+}  // namespace inference

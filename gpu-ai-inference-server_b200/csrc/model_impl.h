@@ -1,0 +1,79 @@
+// model_impl.h — private implementation behind inference::Model (PIMPL), shared with the C bridge
+// so that ModelInfer can hand caller buffers to the GPU without intermediate copies.
+#pragma once
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "model.h"
+#include "plan.h"
+
+namespace inference {
+
+// Borrowed description of one caller tensor (no ownership, no copy).
+struct IoDesc {
+    std::string name;
+    DataType dtype = DataType::FLOAT32;
+    std::vector<int64_t> dims;
+    const void* data = nullptr;  // host memory
+    size_t bytes = 0;
+};
+struct OutDesc {
+    std::string name;           // filled by the engine (graph output name)
+    std::vector<int64_t> dims;  // filled by the engine
+    void* data = nullptr;       // caller buffer (may be null: nothing is copied)
+    size_t capacity = 0;        // bytes available at `data`
+    size_t produced = 0;        // bytes the engine produced for this output
+};
+
+class ModelImpl {
+public:
+    ModelImpl(const std::string& model_path, ModelType type, const ModelConfig& config, DeviceType device, int device_id);
+    ~ModelImpl();
+
+    bool Load();
+    void Unload();
+    bool IsLoaded() const { return loaded_.load(std::memory_order_acquire); }
+    bool Infer(const std::vector<Tensor>& inputs, std::vector<Tensor>& outputs);
+    // Zero-copy variant used by the C bridge.  `outs` has one entry per caller-provided output slot
+    // (matched by POSITION, reference inference_bridge.cpp:794-812).
+    bool InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDesc>& outs);
+
+    ModelMetadata GetMetadata() const;
+    Model::Stats GetStats() const;
+    std::string GetLastError() const;
+    void SetLastError(const std::string& e) const;
+
+    // extension API (b200_engine.h)
+    struct Loaded {
+        std::shared_ptr<const b200::Plan> plan;
+        std::vector<std::unique_ptr<b200::Replica>> replicas;
+        std::vector<float> last_ms;
+    };
+    std::shared_ptr<Loaded> Pin() const;
+    int staged_batch = 0;
+
+private:
+    bool ValidateInputs(const std::vector<IoDesc>& ins) const;
+    bool Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs);
+
+    std::string model_path_;
+    ModelType type_;
+    ModelConfig config_;
+    DeviceType device_type_;
+    int device_id_;
+    std::atomic<bool> loaded_{false};
+    ModelMetadata metadata_;
+    std::atomic<int64_t> inference_count_{0}, total_ns_{0}, last_ns_{0};
+    std::atomic<size_t> memory_bytes_{0};
+    mutable std::mutex err_mu_;
+    mutable std::string last_error_;
+    mutable std::mutex state_mu_;
+    std::shared_ptr<Loaded> state_;
+    std::atomic<unsigned> round_robin_{0};
+};
+
+}  // namespace inference

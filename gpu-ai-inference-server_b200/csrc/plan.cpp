@@ -1,0 +1,962 @@
+// plan.cpp — ONNX graph -> fused static launch plan (see plan.h).
+//
+// Lowering rules (operator semantics: ONNX opset 12, the set listed in SURVEY.md §8 a10):
+//   * Identity / Dropout / one-input Concat           -> aliases, no step
+//   * Concat(axis=1) chains sharing a first input      -> IN PLACE: every member is produced directly
+//     into its channel slice of one block buffer; the Concat node itself emits nothing
+//   * BatchNormalization -> Relu -> Conv               -> folded into the Conv's A-operand prologue
+//     (pre-activation DenseNet layers: every consumer applies its OWN scale/shift to shared features)
+//   * Conv -> Relu                                     -> ReLU in the Conv epilogue
+//   * Conv(1x1) -> AveragePool(2x2,s2) (bf16/fp8 only) -> pooling commuted in front of the conv (both linear)
+//   * BatchNormalization -> Relu -> GlobalAveragePool  -> one fused reduction kernel
+//   * Gemm / MatMul (+Add bias)                        -> Conv step with H = W = 1
+//   * everything else in the supported set             -> standalone step
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+
+namespace b200 {
+
+const char* PrecisionName(Precision p) {
+    switch (p) {
+        case Precision::FP32: return "fp32";
+        case Precision::BF16: return "bf16";
+        case Precision::FP8: return "fp8";
+    }
+    return "?";
+}
+bool ParsePrecision(const std::string& s, Precision* out) {
+    std::string t;
+    for (char c : s) t.push_back((char)tolower(c));
+    if (t == "fp32" || t == "f32" || t == "float32" || t == "tf32") { *out = Precision::FP32; return true; }
+    if (t == "bf16" || t == "bfloat16") { *out = Precision::BF16; return true; }
+    if (t == "fp8" || t == "e4m3" || t == "fp8-e4m3" || t == "fp8_e4m3") { *out = Precision::FP8; return true; }
+    return false;
+}
+const char* DTypeName(DType d) {
+    switch (d) {
+        case DType::F32: return "f32";
+        case DType::BF16: return "bf16";
+        case DType::FP8: return "e4m3";
+        case DType::U8: return "u8";
+    }
+    return "?";
+}
+const char* StepKindName(StepKind k) {
+    switch (k) {
+        case StepKind::NchwToNhwc: return "nchw_to_nhwc";
+        case StepKind::NhwcToNchw: return "nhwc_to_nchw";
+        case StepKind::Conv: return "conv";
+        case StepKind::MaxPool: return "maxpool";
+        case StepKind::AvgPool: return "avgpool";
+        case StepKind::BnRelu: return "bn_relu";
+        case StepKind::GlobalAvgPool: return "global_avgpool";
+        case StepKind::Add: return "add";
+        case StepKind::Relu: return "relu";
+        case StepKind::Softmax: return "softmax";
+        case StepKind::CopyChannels: return "copy_channels";
+    }
+    return "?";
+}
+
+namespace {
+
+struct VShape {
+    int rank = 0;
+    int C = 0, H = 1, W = 1;
+};
+
+[[noreturn]] void Fail(const std::string& msg) { throw std::runtime_error("planner: " + msg); }
+
+struct ConcatGroup {
+    std::vector<std::string> members;  // canonical value names, longest list seen
+    std::vector<int> offs;
+    int total = 0;
+    int buffer = -1;
+    bool inplace = true;
+};
+
+class Lowerer {
+public:
+    Lowerer(const onnx::Model& m, Precision prec, int max_batch) : m_(m), g_(m.graph) {
+        plan_.precision = prec;
+        plan_.max_batch = std::max(1, max_batch);
+        act_dtype_ = prec == Precision::FP32 ? DType::F32 : prec == Precision::BF16 ? DType::BF16 : DType::FP8;
+    }
+
+    Plan Run() {
+        BuildAliasesAndConsumers();
+        InferShapes();
+        PlanConcatGroups();
+        LowerInputs();
+        for (size_t i = 0; i < g_.nodes.size(); ++i) LowerNode((int)i);
+        LowerOutputs();
+        Liveness();
+        Account();
+        return std::move(plan_);
+    }
+
+private:
+    const onnx::Model& m_;
+    const onnx::Graph& g_;
+    Plan plan_;
+    DType act_dtype_;
+
+    std::unordered_map<std::string, std::string> alias_;
+    std::unordered_map<std::string, std::vector<int>> consumers_;
+    std::unordered_map<std::string, int> producer_;
+    std::set<std::string> graph_outputs_;
+    std::unordered_map<std::string, VShape> shapes_;
+    std::vector<ConcatGroup> groups_;
+    std::unordered_map<std::string, std::pair<int, int>> member_of_;  // value -> (group, index)
+    std::unordered_map<int, int> concat_group_of_node_;
+    std::set<int> skipped_;  // nodes folded into a neighbour
+
+    struct Prologue {
+        int src_tensor = -1;
+        int scale = -1, shift = -1;
+        bool relu = false;
+    };
+    std::unordered_map<std::string, Prologue> pending_pre_;  // keyed by the value the consumer reads
+
+    // ------------------------------------------------------------------ helpers
+    std::string Canon(const std::string& n) const {
+        std::string cur = n;
+        for (int guard = 0; guard < 1000; ++guard) {
+            auto it = alias_.find(cur);
+            if (it == alias_.end()) return cur;
+            cur = it->second;
+        }
+        Fail("alias cycle at " + n);
+    }
+    bool IsInit(const std::string& n) const { return g_.initializers.count(n) > 0; }
+    const onnx::TensorConst& Init(const std::string& n) const {
+        auto it = g_.initializers.find(n);
+        if (it == g_.initializers.end()) Fail("expected a constant initializer for '" + n + "'");
+        return it->second;
+    }
+    const std::vector<int>& Consumers(const std::string& canon) const {
+        static const std::vector<int> kEmpty;
+        auto it = consumers_.find(canon);
+        return it == consumers_.end() ? kEmpty : it->second;
+    }
+    // The single non-alias consumer of `canon`, or -1 (also -1 if the value is a graph output).
+    int SoleConsumer(const std::string& canon) const {
+        if (graph_outputs_.count(canon)) return -1;
+        const auto& c = Consumers(canon);
+        return c.size() == 1 ? c[0] : -1;
+    }
+    int AddConst(const std::string& name, std::vector<int64_t> dims, std::vector<float> data) {
+        ConstBlob b;
+        b.name = name;
+        b.dims = std::move(dims);
+        b.data = std::move(data);
+        plan_.consts.push_back(std::move(b));
+        return (int)plan_.consts.size() - 1;
+    }
+    int NewBuffer(size_t elems_per_sample, DType dt, BufferDesc::Role role = BufferDesc::Role::Arena, int io = -1) {
+        BufferDesc b;
+        b.elems_per_sample = elems_per_sample;
+        b.dtype = dt;
+        b.role = role;
+        b.io_index = io;
+        plan_.buffers.push_back(b);
+        return (int)plan_.buffers.size() - 1;
+    }
+    int AddTensor(const TensorDesc& t) {
+        plan_.tensors.push_back(t);
+        return (int)plan_.tensors.size() - 1;
+    }
+    void Bind(const std::string& value, int tensor) { plan_.value_to_tensor[value] = tensor; }
+    int TensorOf(const std::string& value) const {
+        auto it = plan_.value_to_tensor.find(value);
+        if (it == plan_.value_to_tensor.end()) {
+            auto it2 = plan_.value_to_tensor.find(Canon(value));
+            if (it2 == plan_.value_to_tensor.end()) Fail("value '" + value + "' used before it is produced");
+            return it2->second;
+        }
+        return it->second;
+    }
+    DType ActDType(int rank) const { return rank == 4 ? act_dtype_ : DType::F32; }
+
+    // Create the tensor a producer writes.  Honours in-place concat placement.
+    int NewOutput(const std::string& value, const VShape& s, DType dt) {
+        std::string c = Canon(value);
+        TensorDesc t;
+        t.name = value;
+        t.rank = s.rank;
+        t.C = s.C;
+        t.H = s.H;
+        t.W = s.W;
+        t.dtype = dt;
+        auto it = member_of_.find(c);
+        if (it != member_of_.end() && groups_[it->second.first].inplace && s.rank == 4) {
+            ConcatGroup& grp = groups_[it->second.first];
+            if (grp.buffer < 0) grp.buffer = NewBuffer((size_t)s.H * s.W * grp.total, dt);
+            if (plan_.buffers[grp.buffer].dtype != dt) Fail("mixed dtypes inside concat group at " + value);
+            t.buffer = grp.buffer;
+            t.c_off = grp.offs[it->second.second];
+            t.pitch = grp.total;
+        } else {
+            t.buffer = NewBuffer((size_t)s.H * s.W * s.C, dt);
+            t.c_off = 0;
+            t.pitch = s.C;
+        }
+        int idx = AddTensor(t);
+        Bind(value, idx);
+        if (c != value) Bind(c, idx);
+        return idx;
+    }
+    Step& Emit(StepKind k, const std::string& name) {
+        Step s;
+        s.kind = k;
+        s.name = name;
+        plan_.steps.push_back(s);
+        return plan_.steps.back();
+    }
+
+    // ------------------------------------------------------------------ pass 0
+    void BuildAliasesAndConsumers() {
+        for (auto& o : g_.outputs) graph_outputs_.insert(o.name);
+        for (size_t i = 0; i < g_.nodes.size(); ++i) {
+            const auto& n = g_.nodes[i];
+            if (n.outputs.empty()) continue;
+            bool is_alias = (n.op_type == "Identity" || n.op_type == "Dropout") ||
+                            (n.op_type == "Concat" && n.inputs.size() == 1);
+            if (is_alias && !IsInit(n.inputs[0])) alias_[n.outputs[0]] = n.inputs[0];
+            for (auto& o : n.outputs) producer_[o] = (int)i;
+        }
+        // graph outputs that are aliases keep their own identity for by-name lookup; canonicalise the set
+        std::set<std::string> canon_outs;
+        for (auto& o : graph_outputs_) canon_outs.insert(Canon(o));
+        graph_outputs_.insert(canon_outs.begin(), canon_outs.end());
+        for (size_t i = 0; i < g_.nodes.size(); ++i) {
+            const auto& n = g_.nodes[i];
+            if (alias_.count(n.outputs.empty() ? std::string() : n.outputs[0])) continue;
+            for (auto& in : n.inputs) {
+                if (in.empty() || IsInit(in)) continue;
+                consumers_[Canon(in)].push_back((int)i);
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ pass 1
+    VShape ShapeOf(const std::string& v) const {
+        auto it = shapes_.find(Canon(v));
+        if (it == shapes_.end()) Fail("no shape for value '" + v + "'");
+        return it->second;
+    }
+    static int PoolOut(int in, int k, int s, int p0, int p1, bool ceil_mode) {
+        int num = in + p0 + p1 - k;
+        int o = ceil_mode ? (num + s - 1) / s + 1 : num / s + 1;
+        if (ceil_mode && (o - 1) * s >= in + p0) --o;
+        return o;
+    }
+    void InferShapes() {
+        for (auto& vi : g_.inputs) {
+            VShape s;
+            s.rank = (int)vi.dims.size();
+            if (s.rank == 4) {
+                s.C = (int)vi.dims[1]; s.H = (int)vi.dims[2]; s.W = (int)vi.dims[3];
+            } else if (s.rank == 2) {
+                s.C = (int)vi.dims[1];
+            } else {
+                Fail("graph input '" + vi.name + "' has rank " + std::to_string(s.rank) + "; only rank 2 and 4 are supported");
+            }
+            if (s.C <= 0 || s.H <= 0 || s.W <= 0) Fail("graph input '" + vi.name + "' has a dynamic non-batch dimension");
+            shapes_[vi.name] = s;
+        }
+        for (const auto& n : g_.nodes) {
+            if (n.outputs.empty()) continue;
+            const std::string& op = n.op_type;
+            const std::string& out = n.outputs[0];
+            if (alias_.count(out)) continue;
+            VShape s;
+            if (op == "Conv") {
+                VShape x = ShapeOf(n.inputs[0]);
+                const auto& w = Init(n.inputs[1]);
+                if (x.rank != 4 || w.dims.size() != 4) Fail("Conv '" + n.name + "': only 2-D convolutions are supported");
+                auto st = n.GetInts("strides", {1, 1});
+                auto pd = n.GetInts("pads", {0, 0, 0, 0});
+                auto dl = n.GetInts("dilations", {1, 1});
+                if (n.GetInt("group", 1) != 1) Fail("Conv '" + n.name + "': group != 1 is not supported");
+                if (dl[0] != 1 || dl[1] != 1) Fail("Conv '" + n.name + "': dilation != 1 is not supported");
+                if (n.GetStr("auto_pad", "NOTSET") != "NOTSET") Fail("Conv '" + n.name + "': auto_pad is not supported");
+                if (st[0] != st[1] || pd[0] != pd[1] || pd[0] != pd[2] || pd[0] != pd[3])
+                    Fail("Conv '" + n.name + "': only square strides and symmetric pads are supported");
+                if (w.dims[1] != x.C) Fail("Conv '" + n.name + "': weight Cin does not match input channels");
+                s.rank = 4;
+                s.C = (int)w.dims[0];
+                s.H = (x.H + 2 * (int)pd[0] - (int)w.dims[2]) / (int)st[0] + 1;
+                s.W = (x.W + 2 * (int)pd[0] - (int)w.dims[3]) / (int)st[0] + 1;
+            } else if (op == "BatchNormalization" || op == "Relu" || op == "Softmax") {
+                s = ShapeOf(n.inputs[0]);
+            } else if (op == "Concat") {
+                int64_t axis = n.GetInt("axis", 1);
+                s = ShapeOf(n.inputs[0]);
+                if (axis < 0) axis += s.rank;
+                if (axis != 1) Fail("Concat '" + n.name + "': only channel concat (axis=1) is supported");
+                s.C = 0;
+                for (auto& in : n.inputs) {
+                    VShape t = ShapeOf(in);
+                    if (t.rank != s.rank || t.H != s.H || t.W != s.W) Fail("Concat '" + n.name + "': mismatched inputs");
+                    s.C += t.C;
+                }
+            } else if (op == "MaxPool" || op == "AveragePool") {
+                VShape x = ShapeOf(n.inputs[0]);
+                if (x.rank != 4) Fail(op + " expects a rank-4 input");
+                auto k = n.GetInts("kernel_shape");
+                auto st = n.GetInts("strides", {1, 1});
+                auto pd = n.GetInts("pads", {0, 0, 0, 0});
+                if (k.size() != 2 || k[0] != k[1] || st[0] != st[1] || pd[0] != pd[1] || pd[0] != pd[2] || pd[0] != pd[3])
+                    Fail(op + " '" + n.name + "': only square kernels/strides and symmetric pads are supported");
+                if (n.GetStr("auto_pad", "NOTSET") != "NOTSET") Fail(op + ": auto_pad is not supported");
+                bool ceil_mode = n.GetInt("ceil_mode", 0) != 0;
+                s = x;
+                s.H = PoolOut(x.H, (int)k[0], (int)st[0], (int)pd[0], (int)pd[0], ceil_mode);
+                s.W = PoolOut(x.W, (int)k[0], (int)st[0], (int)pd[0], (int)pd[0], ceil_mode);
+            } else if (op == "GlobalAveragePool") {
+                VShape x = ShapeOf(n.inputs[0]);
+                s.rank = 4; s.C = x.C; s.H = 1; s.W = 1;
+            } else if (op == "Flatten") {
+                VShape x = ShapeOf(n.inputs[0]);
+                if (n.GetInt("axis", 1) != 1) Fail("Flatten: only axis=1 is supported");
+                s.rank = 2; s.C = x.C * x.H * x.W;
+            } else if (op == "Gemm") {
+                VShape x = ShapeOf(n.inputs[0]);
+                const auto& w = Init(n.inputs[1]);
+                if (x.rank != 2 || w.dims.size() != 2) Fail("Gemm expects rank-2 operands");
+                if (n.GetInt("transA", 0)) Fail("Gemm: transA is not supported");
+                bool tb = n.GetInt("transB", 0) != 0;
+                int64_t K = tb ? w.dims[1] : w.dims[0], Nn = tb ? w.dims[0] : w.dims[1];
+                if (K != x.C) Fail("Gemm '" + n.name + "': inner dimensions do not match");
+                s.rank = 2; s.C = (int)Nn;
+            } else if (op == "MatMul") {
+                VShape x = ShapeOf(n.inputs[0]);
+                const auto& w = Init(n.inputs[1]);
+                if (x.rank != 2 || w.dims.size() != 2 || w.dims[0] != x.C) Fail("MatMul '" + n.name + "': expects [N,K] x const [K,M]");
+                s.rank = 2; s.C = (int)w.dims[1];
+            } else if (op == "Add") {
+                const std::string& a = IsInit(n.inputs[0]) ? n.inputs[1] : n.inputs[0];
+                s = ShapeOf(a);
+            } else {
+                Fail("unsupported operator '" + op + "' (node '" + n.name + "')");
+            }
+            shapes_[out] = s;
+        }
+    }
+
+    // ------------------------------------------------------------------ pass 2
+    void PlanConcatGroups() {
+        std::unordered_map<std::string, int> by_first;
+        for (size_t i = 0; i < g_.nodes.size(); ++i) {
+            const auto& n = g_.nodes[i];
+            if (n.op_type != "Concat" || n.inputs.size() < 2) continue;
+            std::vector<std::string> ins;
+            for (auto& in : n.inputs) ins.push_back(Canon(in));
+            int gi;
+            auto it = by_first.find(ins[0]);
+            if (it == by_first.end()) {
+                gi = (int)groups_.size();
+                groups_.push_back(ConcatGroup());
+                by_first[ins[0]] = gi;
+                groups_[gi].members = ins;
+            } else {
+                gi = it->second;
+                auto& mem = groups_[gi].members;
+                size_t common = std::min(mem.size(), ins.size());
+                if (!std::equal(mem.begin(), mem.begin() + common, ins.begin())) {
+                    // not a prefix chain: give this Concat its own copy-mode group
+                    gi = (int)groups_.size();
+                    groups_.push_back(ConcatGroup());
+                    groups_[gi].members = ins;
+                    groups_[gi].inplace = false;
+                } else if (ins.size() > mem.size()) {
+                    mem = ins;
+                }
+            }
+            concat_group_of_node_[(int)i] = gi;
+        }
+        for (size_t gi = 0; gi < groups_.size(); ++gi) {
+            auto& grp = groups_[gi];
+            VShape s0 = ShapeOf(grp.members[0]);
+            if (s0.rank != 4) grp.inplace = false;
+            std::set<std::string> seen;
+            for (auto& v : grp.members) {
+                if (!producer_.count(v) || IsInit(v)) grp.inplace = false;          // graph inputs / constants
+                if (member_of_.count(v) || !seen.insert(v).second) grp.inplace = false;  // shared with another group
+                if (producer_.count(v) && g_.nodes[producer_.at(v)].op_type == "Concat") grp.inplace = false;  // nested
+            }
+            grp.offs.clear();
+            grp.total = 0;
+            for (auto& v : grp.members) {
+                grp.offs.push_back(grp.total);
+                grp.total += ShapeOf(v).C;
+            }
+            if (grp.inplace)
+                for (size_t k = 0; k < grp.members.size(); ++k) member_of_[grp.members[k]] = {(int)gi, (int)k};
+        }
+    }
+
+    void LowerInputs() {
+        for (size_t i = 0; i < g_.inputs.size(); ++i) {
+            const auto& vi = g_.inputs[i];
+            if (vi.elem_type != onnx::kFloat) Fail("graph input '" + vi.name + "' must be FLOAT");
+            VShape s = ShapeOf(vi.name);
+            plan_.input_names.push_back(vi.name);
+            std::vector<int64_t> dims = vi.dims;
+            dims[0] = -1;
+            plan_.input_dims.push_back(dims);
+            TensorDesc raw;
+            raw.name = vi.name + "#host";
+            raw.rank = s.rank; raw.C = s.C; raw.H = s.H; raw.W = s.W;
+            raw.dtype = DType::F32;
+            raw.pitch = s.C;
+            raw.buffer = NewBuffer((size_t)s.C * s.H * s.W, DType::F32, BufferDesc::Role::Input, (int)i);
+            int raw_idx = AddTensor(raw);
+            plan_.inputs.push_back(raw_idx);
+            if (s.rank == 2) {
+                Bind(vi.name, raw_idx);
+                continue;
+            }
+            // rank 4: NCHW fp32 as given by the caller -> internal NHWC.  In the tensor-core modes the stem
+            // input is bf16 with channels padded to a multiple of 4 so a pixel is 8-byte addressable.
+            bool lowp = plan_.precision != Precision::FP32;
+            TensorDesc t;
+            t.name = vi.name;
+            t.rank = 4; t.C = s.C; t.H = s.H; t.W = s.W;
+            t.dtype = lowp ? DType::BF16 : DType::F32;
+            t.pitch = lowp ? (s.C + 3) / 4 * 4 : s.C;
+            t.buffer = NewBuffer((size_t)s.H * s.W * t.pitch, t.dtype);
+            int idx = AddTensor(t);
+            Bind(vi.name, idx);
+            Step& st = Emit(StepKind::NchwToNhwc, vi.name);
+            st.in = raw_idx;
+            st.out = idx;
+        }
+    }
+
+    // Folded BatchNormalization constants: y = x * scale + shift.
+    void BnConsts(const onnx::Node& n, int* scale_idx, int* shift_idx) {
+        const auto& sc = Init(n.inputs[1]);
+        const auto& b = Init(n.inputs[2]);
+        const auto& mean = Init(n.inputs[3]);
+        const auto& var = Init(n.inputs[4]);
+        float eps = n.GetFloat("epsilon", 1e-5f);
+        size_t C = sc.f32.size();
+        if (b.f32.size() != C || mean.f32.size() != C || var.f32.size() != C) Fail("BatchNormalization '" + n.name + "': parameter sizes differ");
+        std::vector<float> scale(C), shift(C);
+        for (size_t c = 0; c < C; ++c) {
+            double inv = 1.0 / std::sqrt((double)var.f32[c] + (double)eps);
+            double s = (double)sc.f32[c] * inv;
+            scale[c] = (float)s;
+            shift[c] = (float)((double)b.f32[c] - (double)mean.f32[c] * s);
+        }
+        *scale_idx = AddConst(n.name + ".scale", {(int64_t)C}, std::move(scale));
+        *shift_idx = AddConst(n.name + ".shift", {(int64_t)C}, std::move(shift));
+    }
+
+    void LowerNode(int ni) {
+        if (skipped_.count(ni)) return;
+        const auto& n = g_.nodes[ni];
+        if (n.outputs.empty()) return;
+        const std::string& op = n.op_type;
+        const std::string& out = n.outputs[0];
+        if (alias_.count(out)) return;  // Identity / Dropout / 1-input Concat
+
+        if (op == "Concat") return LowerConcat(ni);
+        if (op == "BatchNormalization") return LowerBatchNorm(ni);
+        if (op == "Conv") return LowerConv(ni);
+        if (op == "Gemm" || op == "MatMul") return LowerGemm(ni);
+        if (op == "MaxPool" || op == "AveragePool") return LowerPool(ni);
+        if (op == "GlobalAveragePool") return LowerGap(ni, Prologue());
+        if (op == "Flatten") return LowerFlatten(ni);
+        if (op == "Relu") {
+            int in = TensorOf(n.inputs[0]);
+            VShape s = ShapeOf(out);
+            int o = NewOutput(out, s, plan_.tensors[in].dtype);
+            Step& st = Emit(StepKind::Relu, n.name.empty() ? out : n.name);
+            st.in = in; st.out = o;
+            return;
+        }
+        if (op == "Softmax") {
+            VShape s = ShapeOf(out);
+            int64_t axis = n.GetInt("axis", m_.opset < 13 ? 1 : -1);
+            if (axis < 0) axis += s.rank;
+            if (s.rank != 2 || axis != 1) Fail("Softmax: only rank-2 input over axis 1 is supported");
+            int in = TensorOf(n.inputs[0]);
+            int o = NewOutput(out, s, DType::F32);
+            Step& st = Emit(StepKind::Softmax, n.name.empty() ? out : n.name);
+            st.in = in; st.out = o;
+            return;
+        }
+        if (op == "Add") return LowerAdd(ni);
+        Fail("unsupported operator '" + op + "'");
+    }
+
+    void LowerConcat(int ni) {
+        const auto& n = g_.nodes[ni];
+        const std::string& out = n.outputs[0];
+        VShape s = ShapeOf(out);
+        ConcatGroup& grp = groups_[concat_group_of_node_.at(ni)];
+        if (grp.inplace) {
+            TensorDesc t;
+            t.name = out;
+            t.rank = 4; t.C = s.C; t.H = s.H; t.W = s.W;
+            int first = TensorOf(n.inputs[0]);
+            t.buffer = plan_.tensors[first].buffer;
+            t.dtype = plan_.tensors[first].dtype;
+            t.c_off = 0;
+            t.pitch = grp.total;
+            if (t.buffer != grp.buffer) Fail("internal: concat group buffer mismatch at " + out);
+            Bind(out, AddTensor(t));
+            ++plan_.inplace_concats;
+            return;
+        }
+        int first = TensorOf(n.inputs[0]);
+        int o = NewOutput(out, s, plan_.tensors[first].dtype);
+        int off = 0;
+        for (auto& in : n.inputs) {
+            int ti = TensorOf(in);
+            TensorDesc slice = plan_.tensors[o];
+            slice.name = out + "#" + std::to_string(off);
+            slice.c_off += off;
+            slice.C = plan_.tensors[ti].C;
+            int si = AddTensor(slice);
+            Step& st = Emit(StepKind::CopyChannels, out);
+            st.in = ti; st.out = si;
+            off += plan_.tensors[ti].C;
+        }
+        ++plan_.copied_concats;
+    }
+
+    void LowerBatchNorm(int ni) {
+        const auto& n = g_.nodes[ni];
+        const std::string out = n.outputs[0];
+        VShape s = ShapeOf(out);
+        int in = TensorOf(n.inputs[0]);
+        int sc, sh;
+        BnConsts(n, &sc, &sh);
+        if ((int)plan_.consts[sc].data.size() != s.C) Fail("BatchNormalization '" + n.name + "': channel count mismatch");
+
+        // look ahead: BN [-> Relu] -> {Conv | GlobalAveragePool}
+        std::string tail = Canon(out);
+        bool relu = false;
+        int relu_node = -1;
+        int c1 = SoleConsumer(tail);
+        if (c1 >= 0 && g_.nodes[c1].op_type == "Relu") {
+            relu = true;
+            relu_node = c1;
+            tail = Canon(g_.nodes[c1].outputs[0]);
+        }
+        int c2 = SoleConsumer(tail);
+        if (c2 >= 0 && s.rank == 4) {
+            const auto& cn = g_.nodes[c2];
+            bool conv_ok = cn.op_type == "Conv" && Canon(cn.inputs[0]) == tail;
+            bool gap_ok = cn.op_type == "GlobalAveragePool";
+            if (conv_ok || gap_ok) {
+                Prologue p;
+                p.src_tensor = in; p.scale = sc; p.shift = sh; p.relu = relu;
+                if (relu_node >= 0) skipped_.insert(relu_node);
+                if (conv_ok) {
+                    pending_pre_[tail] = p;
+                } else {
+                    skipped_.insert(c2);
+                    LowerGap(c2, p);
+                }
+                return;
+            }
+        }
+        // standalone BN (+ReLU)
+        std::string produced = out;
+        if (relu_node >= 0) {
+            skipped_.insert(relu_node);
+            produced = g_.nodes[relu_node].outputs[0];
+        }
+        int o = NewOutput(produced, s, plan_.tensors[in].dtype);
+        if (produced != out) Bind(out, o);
+        Step& st = Emit(StepKind::BnRelu, n.name.empty() ? out : n.name);
+        st.in = in; st.out = o; st.bn_scale = sc; st.bn_shift = sh; st.relu = relu;
+    }
+
+    void LowerConv(int ni) {
+        const auto& n = g_.nodes[ni];
+        const auto& w = Init(n.inputs[1]);
+        int Cout = (int)w.dims[0], Cin = (int)w.dims[1], R = (int)w.dims[2], S = (int)w.dims[3];
+        int stride = (int)n.GetInts("strides", {1, 1})[0];
+        int pad = (int)n.GetInts("pads", {0, 0, 0, 0})[0];
+
+        Step st;
+        st.kind = StepKind::Conv;
+        st.name = n.name.empty() ? n.outputs[0] : n.name;
+        st.R = R; st.S = S; st.stride = stride; st.pad = pad; st.Cin = Cin; st.Cout = Cout;
+
+        std::string in_name = Canon(n.inputs[0]);
+        auto pit = pending_pre_.find(in_name);
+        if (pit != pending_pre_.end()) {
+            st.in = pit->second.src_tensor;
+            st.pre_scale = pit->second.scale;
+            st.pre_shift = pit->second.shift;
+            st.pre_relu = pit->second.relu;
+            pending_pre_.erase(pit);
+        } else {
+            st.in = TensorOf(n.inputs[0]);
+        }
+
+        // weights: OIHW -> [Cout][R][S][Cin]
+        std::vector<float> packed((size_t)Cout * R * S * Cin);
+        for (int o = 0; o < Cout; ++o)
+            for (int c = 0; c < Cin; ++c)
+                for (int r = 0; r < R; ++r)
+                    for (int s = 0; s < S; ++s)
+                        packed[(((size_t)o * R + r) * S + s) * Cin + c] = w.f32[(((size_t)o * Cin + c) * R + r) * S + s];
+        st.weight = AddConst(n.inputs[1], {Cout, R, S, Cin}, std::move(packed));
+        if (n.inputs.size() > 2 && !n.inputs[2].empty()) {
+            const auto& b = Init(n.inputs[2]);
+            if ((int)b.f32.size() != Cout) Fail("Conv '" + n.name + "': bias size mismatch");
+            st.bias = AddConst(n.inputs[2], {Cout}, b.f32);
+        }
+
+        // epilogue look-ahead
+        std::string produced = n.outputs[0];
+        VShape os = ShapeOf(produced);
+        int c1 = SoleConsumer(Canon(produced));
+        if (c1 >= 0 && g_.nodes[c1].op_type == "Relu" && !skipped_.count(c1)) {
+            st.post_relu = true;
+            skipped_.insert(c1);
+            produced = g_.nodes[c1].outputs[0];
+            c1 = SoleConsumer(Canon(produced));
+        }
+        if (plan_.precision != Precision::FP32 && !st.post_relu && R == 1 && S == 1 && stride == 1 && pad == 0 &&
+            c1 >= 0 && g_.nodes[c1].op_type == "AveragePool" && !skipped_.count(c1)) {
+            const auto& pn = g_.nodes[c1];
+            auto k = pn.GetInts("kernel_shape");
+            auto pst = pn.GetInts("strides", {1, 1});
+            auto ppd = pn.GetInts("pads", {0, 0, 0, 0});
+            VShape xs = ShapeOf(n.outputs[0]);
+            if (k[0] == 2 && pst[0] == 2 && ppd[0] == 0 && xs.H % 2 == 0 && xs.W % 2 == 0) {
+                // avgpool(conv1x1(x)) == conv1x1(avgpool(x)); 4x fewer GEMM rows
+                st.pool2_fused = true;
+                skipped_.insert(c1);
+                produced = pn.outputs[0];
+                os = ShapeOf(produced);
+            }
+        }
+        st.out = NewOutput(produced, os, ActDType(4));
+        if (produced != n.outputs[0] && !st.pool2_fused) Bind(n.outputs[0], st.out);
+        plan_.steps.push_back(st);
+    }
+
+    void LowerGemm(int ni) {
+        const auto& n = g_.nodes[ni];
+        const auto& w = Init(n.inputs[1]);
+        bool gemm = n.op_type == "Gemm";
+        bool tb = gemm && n.GetInt("transB", 0) != 0;
+        float alpha = gemm ? n.GetFloat("alpha", 1.f) : 1.f;
+        float beta = gemm ? n.GetFloat("beta", 1.f) : 1.f;
+        int K = (int)(tb ? w.dims[1] : w.dims[0]);
+        int Nn = (int)(tb ? w.dims[0] : w.dims[1]);
+
+        Step st;
+        st.kind = StepKind::Conv;
+        st.name = n.name.empty() ? n.outputs[0] : n.name;
+        st.R = st.S = 1; st.stride = 1; st.pad = 0; st.Cin = K; st.Cout = Nn;
+        st.in = TensorOf(n.inputs[0]);
+        std::vector<float> packed((size_t)Nn * K);
+        for (int o = 0; o < Nn; ++o)
+            for (int k = 0; k < K; ++k)
+                packed[(size_t)o * K + k] = alpha * (tb ? w.f32[(size_t)o * K + k] : w.f32[(size_t)k * Nn + o]);
+        st.weight = AddConst(n.inputs[1], {Nn, 1, 1, K}, std::move(packed));
+        if (gemm && n.inputs.size() > 2 && !n.inputs[2].empty()) {
+            const auto& c = Init(n.inputs[2]);
+            std::vector<float> bias(Nn);
+            if ((int)c.f32.size() == Nn) for (int i = 0; i < Nn; ++i) bias[i] = beta * c.f32[i];
+            else if (c.f32.size() == 1) for (int i = 0; i < Nn; ++i) bias[i] = beta * c.f32[0];
+            else Fail("Gemm '" + n.name + "': C must be a scalar or a vector of length N");
+            st.bias = AddConst(n.inputs[2], {Nn}, std::move(bias));
+        }
+        std::string produced = n.outputs[0];
+        // MatMul -> Add(const vector) folds into the bias
+        int c1 = SoleConsumer(Canon(produced));
+        if (st.bias < 0 && c1 >= 0 && g_.nodes[c1].op_type == "Add") {
+            const auto& an = g_.nodes[c1];
+            int ci = IsInit(an.inputs[0]) ? 0 : IsInit(an.inputs[1]) ? 1 : -1;
+            if (ci >= 0 && (int)Init(an.inputs[ci]).f32.size() == Nn) {
+                st.bias = AddConst(an.inputs[ci], {Nn}, Init(an.inputs[ci]).f32);
+                skipped_.insert(c1);
+                produced = an.outputs[0];
+                c1 = SoleConsumer(Canon(produced));
+            }
+        }
+        if (c1 >= 0 && g_.nodes[c1].op_type == "Relu" && !skipped_.count(c1)) {
+            st.post_relu = true;
+            skipped_.insert(c1);
+            produced = g_.nodes[c1].outputs[0];
+        }
+        VShape os = ShapeOf(produced);
+        st.out = NewOutput(produced, os, DType::F32);
+        plan_.steps.push_back(st);
+    }
+
+    void LowerPool(int ni) {
+        const auto& n = g_.nodes[ni];
+        bool is_max = n.op_type == "MaxPool";
+        int in = TensorOf(n.inputs[0]);
+        VShape s = ShapeOf(n.outputs[0]);
+        int o = NewOutput(n.outputs[0], s, plan_.tensors[in].dtype);
+        Step& st = Emit(is_max ? StepKind::MaxPool : StepKind::AvgPool, n.name.empty() ? n.outputs[0] : n.name);
+        st.in = in; st.out = o;
+        st.R = st.S = (int)n.GetInts("kernel_shape")[0];
+        st.stride = (int)n.GetInts("strides", {1, 1})[0];
+        st.pad = (int)n.GetInts("pads", {0, 0, 0, 0})[0];
+        st.count_include_pad = n.GetInt("count_include_pad", 0) != 0;
+        st.ceil_mode = n.GetInt("ceil_mode", 0) != 0;
+    }
+
+    void LowerGap(int ni, const Prologue& p) {
+        const auto& n = g_.nodes[ni];
+        int in = p.src_tensor >= 0 ? p.src_tensor : TensorOf(n.inputs[0]);
+        VShape s = ShapeOf(n.outputs[0]);
+        int o = NewOutput(n.outputs[0], s, DType::F32);
+        Step& st = Emit(StepKind::GlobalAvgPool, n.name.empty() ? n.outputs[0] : n.name);
+        st.in = in; st.out = o;
+        st.bn_scale = p.scale; st.bn_shift = p.shift; st.relu = p.relu;
+    }
+
+    void LowerFlatten(int ni) {
+        const auto& n = g_.nodes[ni];
+        int in = TensorOf(n.inputs[0]);
+        const TensorDesc& x = plan_.tensors[in];
+        VShape s = ShapeOf(n.outputs[0]);
+        if (x.rank == 2 || (x.H == 1 && x.W == 1)) {
+            TensorDesc t = x;
+            t.name = n.outputs[0];
+            t.rank = 2; t.H = t.W = 1;
+            Bind(n.outputs[0], AddTensor(t));
+            return;
+        }
+        int o = NewOutput(n.outputs[0], s, DType::F32);
+        Step& st = Emit(StepKind::NhwcToNchw, n.name.empty() ? n.outputs[0] : n.name);
+        st.in = in; st.out = o;
+    }
+
+    void LowerAdd(int ni) {
+        const auto& n = g_.nodes[ni];
+        int ci = IsInit(n.inputs[0]) ? 0 : IsInit(n.inputs[1]) ? 1 : -1;
+        VShape s = ShapeOf(n.outputs[0]);
+        if (ci >= 0) {
+            // x + const vector over channels  ==  BnRelu step with scale 1
+            const auto& c = Init(n.inputs[ci]);
+            int in = TensorOf(n.inputs[1 - ci]);
+            std::vector<float> shift(s.C);
+            if ((int)c.f32.size() == s.C) shift = c.f32;
+            else if (c.f32.size() == 1) std::fill(shift.begin(), shift.end(), c.f32[0]);
+            else Fail("Add '" + n.name + "': constant operand must broadcast over channels");
+            int sc = AddConst(n.name + ".one", {s.C}, std::vector<float>(s.C, 1.f));
+            int sh = AddConst(n.inputs[ci], {s.C}, std::move(shift));
+            int o = NewOutput(n.outputs[0], s, plan_.tensors[in].dtype);
+            Step& st = Emit(StepKind::BnRelu, n.name.empty() ? n.outputs[0] : n.name);
+            st.in = in; st.out = o; st.bn_scale = sc; st.bn_shift = sh; st.relu = false;
+            return;
+        }
+        int a = TensorOf(n.inputs[0]), b = TensorOf(n.inputs[1]);
+        VShape sa = ShapeOf(n.inputs[0]), sb = ShapeOf(n.inputs[1]);
+        if (sa.rank != sb.rank || sa.C != sb.C || sa.H != sb.H || sa.W != sb.W) Fail("Add '" + n.name + "': broadcasting between activations is not supported");
+        int o = NewOutput(n.outputs[0], s, plan_.tensors[a].dtype);
+        Step& st = Emit(StepKind::Add, n.name.empty() ? n.outputs[0] : n.name);
+        st.in = a; st.in2 = b; st.out = o;
+    }
+
+    void LowerOutputs() {
+        for (size_t i = 0; i < g_.outputs.size(); ++i) {
+            const auto& vi = g_.outputs[i];
+            int ti = TensorOf(vi.name);
+            const TensorDesc t = plan_.tensors[ti];
+            plan_.output_names.push_back(vi.name);
+            std::vector<int64_t> dims;
+            if (t.rank == 4) dims = {-1, t.C, t.H, t.W};
+            else dims = {-1, t.C};
+            plan_.output_dims.push_back(dims);
+            BufferDesc& b = plan_.buffers[t.buffer];
+            bool direct = t.dtype == DType::F32 && t.c_off == 0 && t.pitch == t.C && (t.rank == 2 || t.H * t.W == 1) &&
+                          b.role == BufferDesc::Role::Arena && b.elems_per_sample == (size_t)t.C;
+            if (direct) {
+                b.role = BufferDesc::Role::Output;
+                b.io_index = (int)i;
+                plan_.outputs.push_back(ti);
+                continue;
+            }
+            TensorDesc o;
+            o.name = vi.name + "#host";
+            o.rank = t.rank; o.C = t.C; o.H = t.H; o.W = t.W;
+            o.dtype = DType::F32;
+            o.pitch = t.C;
+            o.buffer = NewBuffer((size_t)t.C * t.H * t.W, DType::F32, BufferDesc::Role::Output, (int)i);
+            int oi = AddTensor(o);
+            Step& st = Emit(StepKind::NhwcToNchw, vi.name);
+            st.in = ti; st.out = oi;
+            plan_.outputs.push_back(oi);
+        }
+    }
+
+    // ------------------------------------------------------------------ arena
+    void Liveness() {
+        const int nsteps = (int)plan_.steps.size();
+        auto touch = [&](int tensor, int step) {
+            if (tensor < 0) return;
+            BufferDesc& b = plan_.buffers[plan_.tensors[tensor].buffer];
+            b.first_step = std::min(b.first_step, step);
+            b.last_step = std::max(b.last_step, step);
+        };
+        for (int s = 0; s < nsteps; ++s) {
+            touch(plan_.steps[s].in, s);
+            touch(plan_.steps[s].in2, s);
+            touch(plan_.steps[s].out, s);
+        }
+        const char* no_reuse = getenv("B200_ENGINE_NO_REUSE");  // debugging: keep every intermediate value alive
+        for (auto& b : plan_.buffers) {
+            if (no_reuse && no_reuse[0] == '1') { b.first_step = -1; b.last_step = nsteps; }
+            if (b.role == BufferDesc::Role::Input) b.first_step = -1;
+            if (b.role == BufferDesc::Role::Output) b.last_step = nsteps;
+            if (b.last_step < 0) { b.first_step = -1; b.last_step = nsteps; }  // untouched (pass-through)
+            if (b.role == BufferDesc::Role::Input && b.last_step < 0) b.last_step = nsteps;
+        }
+        // first-fit over live ranges
+        std::vector<int> order(plan_.buffers.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return plan_.buffers[a].first_step < plan_.buffers[b].first_step;
+        });
+        const size_t kAlign = 1024;
+        auto bytes_of = [&](const BufferDesc& b) {
+            size_t n = b.BytesPerSample() * (size_t)plan_.max_batch;
+            return (n + kAlign - 1) / kAlign * kAlign + kAlign;  // +1 KiB guard for vector tails
+        };
+        std::vector<int> placed;
+        size_t top = 0;
+        for (int bi : order) {
+            BufferDesc& b = plan_.buffers[bi];
+            size_t need = bytes_of(b);
+            std::vector<std::pair<size_t, size_t>> busy;
+            for (int pj : placed) {
+                const BufferDesc& q = plan_.buffers[pj];
+                if (q.last_step < b.first_step || b.last_step < q.first_step) continue;
+                busy.push_back({q.offset, q.offset + bytes_of(q)});
+            }
+            std::sort(busy.begin(), busy.end());
+            size_t off = 0;
+            for (auto& iv : busy) {
+                if (off + need <= iv.first) break;
+                off = std::max(off, iv.second);
+            }
+            b.offset = off;
+            top = std::max(top, off + need);
+            placed.push_back(bi);
+        }
+        plan_.arena_bytes = top;
+    }
+
+    void Account() {
+        double flops = 0, bytes = 0;
+        size_t wbytes = 0;
+        for (auto& st : plan_.steps) {
+            const TensorDesc* in = st.in >= 0 ? &plan_.tensors[st.in] : nullptr;
+            const TensorDesc* out = st.out >= 0 ? &plan_.tensors[st.out] : nullptr;
+            double in_b = in ? (double)in->PixelsPerSample() * in->C * DTypeSize(in->dtype) : 0;
+            double out_b = out ? (double)out->PixelsPerSample() * out->C * DTypeSize(out->dtype) : 0;
+            if (st.kind == StepKind::Conv) {
+                // algorithmic FLOPs of the ONNX-order computation (conv before the fused pool)
+                double opix = (double)out->PixelsPerSample() * (st.pool2_fused ? 4.0 : 1.0);
+                st.flops = 2.0 * opix * st.Cout * st.R * st.S * st.Cin;
+                in_b = (double)in->PixelsPerSample() * st.Cin * DTypeSize(in->dtype);
+                wbytes += (size_t)st.Cout * st.R * st.S * st.Cin * (in->dtype == DType::F32 ? 4 : DTypeSize(in->dtype));
+            } else if (st.kind == StepKind::Add) {
+                in_b *= 2;
+            }
+            st.bytes = in_b + out_b;
+            flops += st.flops;
+            bytes += st.bytes;
+        }
+        plan_.flops_per_sample = flops;
+        plan_.hbm_bytes_per_sample = bytes;
+        plan_.weight_bytes = wbytes;
+    }
+};
+
+void JsonEscape(std::ostringstream& os, const std::string& s) {
+    os << '"';
+    for (char c : s) {
+        if (c == '"' || c == '\\') os << '\\' << c;
+        else if ((unsigned char)c < 0x20) os << ' ';
+        else os << c;
+    }
+    os << '"';
+}
+
+}  // namespace
+
+Plan BuildPlan(const onnx::Model& model, Precision precision, int max_batch) {
+    return Lowerer(model, precision, max_batch).Run();
+}
+
+std::string Plan::ToJson() const {
+    std::ostringstream os;
+    os.precision(17);
+    os << "{\"precision\":\"" << PrecisionName(precision) << "\",\"max_batch\":" << max_batch
+       << ",\"arena_bytes\":" << arena_bytes << ",\"weight_bytes\":" << weight_bytes
+       << ",\"flops_per_sample\":" << flops_per_sample << ",\"hbm_bytes_per_sample\":" << hbm_bytes_per_sample
+       << ",\"inplace_concats\":" << inplace_concats << ",\"copied_concats\":" << copied_concats
+       << ",\"num_buffers\":" << buffers.size() << ",\"inputs\":[";
+    for (size_t i = 0; i < input_names.size(); ++i) {
+        if (i) os << ',';
+        os << "{\"name\":";
+        JsonEscape(os, input_names[i]);
+        os << ",\"dims\":[";
+        for (size_t k = 0; k < input_dims[i].size(); ++k) os << (k ? "," : "") << input_dims[i][k];
+        os << "]}";
+    }
+    os << "],\"outputs\":[";
+    for (size_t i = 0; i < output_names.size(); ++i) {
+        if (i) os << ',';
+        os << "{\"name\":";
+        JsonEscape(os, output_names[i]);
+        os << ",\"dims\":[";
+        for (size_t k = 0; k < output_dims[i].size(); ++k) os << (k ? "," : "") << output_dims[i][k];
+        os << "]}";
+    }
+    os << "],\"steps\":[";
+    for (size_t i = 0; i < steps.size(); ++i) {
+        const Step& s = steps[i];
+        if (i) os << ',';
+        os << "{\"i\":" << i << ",\"kind\":\"" << StepKindName(s.kind) << "\",\"name\":";
+        JsonEscape(os, s.name);
+        auto tens = [&](const char* key, int t) {
+            if (t < 0) return;
+            const TensorDesc& d = tensors[t];
+            os << ",\"" << key << "\":{\"buf\":" << d.buffer << ",\"C\":" << d.C << ",\"H\":" << d.H << ",\"W\":" << d.W
+               << ",\"c_off\":" << d.c_off << ",\"pitch\":" << d.pitch << ",\"dtype\":\"" << DTypeName(d.dtype) << "\"}";
+        };
+        tens("in", s.in);
+        tens("in2", s.in2);
+        tens("out", s.out);
+        if (s.kind == StepKind::Conv)
+            os << ",\"R\":" << s.R << ",\"S\":" << s.S << ",\"stride\":" << s.stride << ",\"pad\":" << s.pad
+               << ",\"Cin\":" << s.Cin << ",\"Cout\":" << s.Cout << ",\"pre_bn\":" << (s.pre_scale >= 0 ? "true" : "false")
+               << ",\"pre_relu\":" << (s.pre_relu ? "true" : "false") << ",\"bias\":" << (s.bias >= 0 ? "true" : "false")
+               << ",\"post_relu\":" << (s.post_relu ? "true" : "false") << ",\"pool2_fused\":" << (s.pool2_fused ? "true" : "false");
+        if (s.kind == StepKind::MaxPool || s.kind == StepKind::AvgPool)
+            os << ",\"k\":" << s.R << ",\"stride\":" << s.stride << ",\"pad\":" << s.pad;
+        if (s.kind == StepKind::BnRelu || s.kind == StepKind::GlobalAvgPool)
+            os << ",\"bn\":" << (s.bn_scale >= 0 ? "true" : "false") << ",\"relu\":" << (s.relu ? "true" : "false");
+        os << ",\"flops\":" << s.flops << ",\"bytes\":" << s.bytes << "}";
+    }
+    os << "]}";
+    return os.str();
+}
+
+}  // namespace b200

@@ -1,0 +1,59 @@
+/*
+ * b200_engine.h — extension entry points of libinference_engine.so that the reference ABI has
+ * no slot for.  Nothing here is needed by the Go server; these exist for measurement
+ * (bench.py), parity tests and plan inspection.  Plain C types only.
+ *
+ * Precision selection (no slot in reference ModelConfig, see SURVEY.md §5 "Config / flags"):
+ *   env B200_ENGINE_PRECISION = fp32 | bf16 | fp8      (default fp32), read at Model::Load;
+ *   env B200_ENGINE_DEVICES   = "all" | "0,2,3"        (default: all visible GPUs);
+ *   env B200_ENGINE_MAX_BATCH = per-GPU arena batch     (default 256).
+ *   `config.json` next to model.onnx may carry "precision" / "max_batch_size" with the same
+ *   meaning (environment wins).
+ */
+#ifndef B200_ENGINE_H
+#define B200_ENGINE_H
+
+#include "inference_bridge.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Version string of the engine build ("b200-engine <n> sm_100a"). Static storage. */
+const char* B200EngineVersion(void);
+
+/* Parse + plan `<model_dir>/model.onnx` for `precision` and `max_batch` WITHOUT touching CUDA and
+ * return a malloc'd JSON description (steps, buffers, arena bytes, algorithmic FLOPs and HBM bytes
+ * per image).  NULL + *error on failure.  Caller frees with free(). */
+char* B200PlanDescribe(const char* model_dir, const char* precision, int max_batch, ErrorMessage* error);
+
+/* Number of kernels this library has launched in this process since load (all streams/devices). */
+uint64_t B200KernelLaunchCount(void);
+
+/* Device-resident forward: input `input_name` must already have been staged with
+ * B200ModelStageInput (host -> device copy happens there, outside the timed region).  Runs
+ * `iters` forwards of batch `batch` on every replica of the model concurrently (each replica gets
+ * the same staged batch) and writes per-iteration device time in milliseconds (CUDA events on the
+ * replica's own stream, max over replicas) to ms_out[0..iters).  If l2_flush != 0 a buffer larger
+ * than L2 is overwritten between iterations (outside the event pair). */
+bool B200ModelStageInput(ModelHandle handle, const TensorData* input, ErrorMessage* error);
+bool B200ModelForwardDevice(ModelHandle handle, int batch, int iters, int l2_flush, float* ms_out,
+                            ErrorMessage* error);
+/* Copies the logits of the last B200ModelForwardDevice from replica 0 into `out` (fp32). */
+bool B200ModelReadOutput(ModelHandle handle, float* out, size_t out_elems, ErrorMessage* error);
+
+/* Per-step device timing of one forward at `batch` on replica 0 (events between steps).
+ * Returns malloc'd JSON [{"step":i,"kind":"conv","name":"…","ms":…,"flops":…,"bytes":…},…]. */
+char* B200ModelProfileSteps(ModelHandle handle, int batch, int repeats, ErrorMessage* error);
+
+/* Debug/parity: copy the device tensor that holds ONNX value `value_name` after the last forward on
+ * replica 0 back to host as fp32 NCHW (or row-major 2D).  `out_elems` is the capacity of `out`;
+ * returns the number of elements written, or -1 on error. */
+int64_t B200ModelReadValue(ModelHandle handle, const char* value_name, float* out, size_t out_elems,
+                           ErrorMessage* error);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* B200_ENGINE_H */
