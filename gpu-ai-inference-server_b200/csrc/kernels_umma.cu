@@ -1,8 +1,639 @@
-// placeholder, replaced below
+// kernels_umma.cu — implicit-GEMM convolution on Blackwell 5th-gen tensor cores (sm_100a only).
+//
+//   D[M = n*Ho*Wo pixels][Cout] = A[M][K = taps * Cin] * W[Cout][K]^T          (fp32 accumulate)
+//
+// One persistent CTA per SM, 14 warps, warp-specialised:
+//   warps 0-3, 4-7  A producers (two groups alternating K chunks): coalesced 128-bit global loads of
+//                   NHWC channel slices -> fused prologue (folded BatchNorm scale/shift + ReLU of the
+//                   pre-activation DenseNet layer, optional 2x2 average pooling of the transition)
+//                   -> st.shared into the 128-byte-swizzled K-major UMMA operand layout.
+//   warps 8-11      epilogue: tcgen05.ld the fp32 accumulator out of TMEM, per-channel dequant scale
+//                   + bias + ReLU, convert (bf16 / e4m3), 128-bit stores into the output's channel
+//                   slice (dense-block concat in place).
+//   warp 12         B producer: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) of the packed weights.
+//   warp 13         MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=32 bytes per step),
+//                   tcgen05.commit releases smem stages / publishes the accumulator.
+// Pipelines: NS smem stages (full/empty mbarriers) and 2 TMEM accumulators (full/empty mbarriers), so
+// the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Why A is not loaded by TMA: every dense layer applies its OWN BatchNorm+ReLU to the shared concat
+// buffer (pre-activation), so the A tile has to pass through registers anyway; loading it there
+// directly saves one shared-memory round trip and makes zero padding, the 2x2 pooling and the 7x7
+// stem gather trivial.  Weights (B) have no such transform and do use TMA.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+
 #include "kernels.h"
-namespace b200 { namespace kernels {
+
+namespace b200 {
+namespace kernels {
+
+namespace {
+
+constexpr int kThreads = 448;
+constexpr int kTileM = 128;
+constexpr int kRowBytes = 128;             // one K chunk of one row: 128 bytes (the swizzle span)
+constexpr int kATileBytes = kTileM * kRowBytes;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t SmemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void MbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void MbarArrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void MbarArriveExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(SmemAddr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A lost arrive must become an error, not a hung GPU: trap after a generous spin budget.
+__device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!MbarTryWait(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("conv_umma: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void FenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void TcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void TmaLoad2D(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void PrefetchTensorMap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void TmemAlloc(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void TmemDealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; KIND 0: kind::f16 (bf16 operands), 1: kind::f8f6f4 (e4m3 operands)
+template <int KIND>
+__device__ __forceinline__ void UmmaSS(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void UmmaCommit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemAddr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void TmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t MakeSmemDesc(uint32_t smem_byte_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6) | a_format [7,10) |
+// b_format [10,13) | a/b K-major (0) | N>>3 [17,23) | M>>4 [24,29).
+__host__ __device__ constexpr uint32_t MakeInstrDesc(int fmt, int n) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint4 LdgNc(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 LdgNc8(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void StsV4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------ element traits
+template <typename T> struct MmaElem;
+template <> struct MmaElem<__nv_bfloat16> {
+    static constexpr int kKind = 0, kFmt = 1;  // kind::f16, BF16
+    static constexpr int kPerVec = 8;          // elements per 16 bytes
+    static constexpr int kChunk = 64;          // elements per 128-byte K chunk
+    static constexpr int kStepK = 16;          // elements per tcgen05.mma (32 bytes)
+    __device__ static void Unpack(const uint4& v, float* f) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+    }
+    __device__ static uint4 Pack(const float* f) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+template <> struct MmaElem<__nv_fp8_e4m3> {
+    static constexpr int kKind = 1, kFmt = 0;  // kind::f8f6f4, E4M3
+    static constexpr int kPerVec = 16;
+    static constexpr int kChunk = 128;
+    static constexpr int kStepK = 32;
+    __device__ static void Unpack(const uint4& v, float* f) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * h)) & 0xFFFFu), __NV_E4M3);
+                float2 t = __half22float2(*reinterpret_cast<__half2*>(&hr));
+                f[4 * i + 2 * h] = t.x;
+                f[4 * i + 2 * h + 1] = t.y;
+            }
+        }
+    }
+    __device__ static uint4 Pack(const float* f) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i], f[4 * i + 1]), __NV_SATFINITE, __NV_E4M3);
+            uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i + 2], f[4 * i + 3]), __NV_SATFINITE, __NV_E4M3);
+            w[i] = lo | (hi << 16);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+struct UParams {
+    const void* in;
+    void* out;
+    const float* pre_scale;
+    const float* pre_shift;
+    const float* out_scale;
+    const float* bias;
+    int pre_relu, post_relu;
+    int H, W, in_pitch, in_coff;
+    int Ho, Wo, out_pitch, out_coff, Cout;
+    int Cin, R, S, stride, pad;
+    int M;
+    int num_m_tiles, num_n_tiles;
+    int chunks_per_tap, num_chunks;
+};
+
+enum : int { kModeGeneric = 0, kModePool2 = 1, kModeStem = 2 };
+
+template <int BN> struct TileCfg {
+    static constexpr int kStageBytes = kATileBytes + BN * kRowBytes;
+    static constexpr int kStages = BN == 128 ? 6 : 8;
+    static constexpr int kTmemCols = BN == 128 ? 256 : BN == 64 ? 128 : 64;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------ the kernel
+template <typename MmaT, typename OutT, int BN, int MODE>
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const UParams p) {
+    using ME = MmaElem<MmaT>;
+    using Cfg = TileCfg<BN>;
+    constexpr int NS = Cfg::kStages;
+    constexpr int EPV = ME::kPerVec;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + NS;
+    uint64_t* tmem_full = empty_bar + NS;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    if (warp == 12 && lane == 0) {
+        for (int s = 0; s < NS; ++s) {
+            MbarInit(&full_bar[s], 128 + 1);  // 128 A-producer threads + the TMA thread's expect_tx arrive
+            MbarInit(&empty_bar[s], 1);       // tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            MbarInit(&tmem_full[a], 1);
+            MbarInit(&tmem_empty[a], 128);
+        }
+        FenceBarrierInit();
+        PrefetchTensorMap(&tmap_w);
+    }
+    if (warp == 13) TmemAlloc(tmem_slot, Cfg::kTmemCols);
+    TcFenceBefore();
+    __syncthreads();
+    TcFenceAfter();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // =========================================================== A producers
+        const int group = warp >> 2;
+        const int pt = threadIdx.x & 127;
+        const int sub = pt & 7;     // which 16-byte piece of the 128-byte row
+        const int rbase = pt >> 3;  // rows rbase + 16*i
+        const MmaT* in = reinterpret_cast<const MmaT*>(p.in);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.num_n_tiles;
+            int pix[8];   // input pixel index of tap (0,0) before padding offset, or -1 for rows past M
+            int oyx[8];   // (iy0 << 16) | (ix0 & 0xFFFF): top-left input coordinate of the receptive field
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int m = m_tile * kTileM + rbase + 16 * i;
+                if (m < p.M) {
+                    int ox = m % p.Wo, oy = (m / p.Wo) % p.Ho, img = m / (p.Wo * p.Ho);
+                    int iy0 = (MODE == kModePool2) ? oy * 2 : oy * p.stride - p.pad;
+                    int ix0 = (MODE == kModePool2) ? ox * 2 : ox * p.stride - p.pad;
+                    pix[i] = img * p.H * p.W;
+                    oyx[i] = (int)(((unsigned)iy0 << 16) | ((unsigned)ix0 & 0xFFFFu));
+                } else {
+                    pix[i] = -1;
+                    oyx[i] = 0;
+                }
+            }
+            for (int c = 0; c < p.num_chunks; ++c, ++it) {
+                if ((int)(it & 1u) != group) continue;
+                const int stage = it % NS;
+                const uint32_t phase = (it / NS) & 1u;
+                const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
+                uint4 v[8];
+                if (MODE == kModeStem) {
+                    // chunk c = filter rows 2c, 2c+1; a row is 8 pixels x 4 channels (64 B); this thread owns
+                    // 2 pixels of one filter row: piece = sub & 3, filter row = 2c + (sub >> 2)
+                    const int r = 2 * c + (sub >> 2);
+                    const int dx = 2 * (sub & 3);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
+                        if (pix[i] >= 0 && r < p.R) {
+                            int iy = (oyx[i] >> 16) + r;
+                            int ix = (int)(short)(oyx[i] & 0xFFFF) + dx;
+                            if (iy >= 0 && iy < p.H) {
+                                const MmaT* row = in + ((size_t)pix[i] + (size_t)iy * p.W) * p.in_pitch;
+                                if (ix >= 0 && ix < p.W) a = LdgNc8(row + (size_t)ix * p.in_pitch);
+                                if (ix + 1 >= 0 && ix + 1 < p.W) b = LdgNc8(row + (size_t)(ix + 1) * p.in_pitch);
+                            }
+                        }
+                        v[i] = make_uint4(a.x, a.y, b.x, b.y);
+                    }
+                    MbarWait(&empty_bar[stage], phase ^ 1u);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        int row = rbase + 16 * i;
+                        StsV4(a_base + row * kRowBytes + ((sub ^ (row & 7)) << 4), v[i]);
+                    }
+                } else {
+                    const int tap = c / p.chunks_per_tap, j = c - tap * p.chunks_per_tap;
+                    const int fr = tap / p.S, fs = tap - fr * p.S;
+                    const int ch0 = j * ME::kChunk + sub * EPV;
+                    const bool ch_ok = ch0 < p.Cin;
+                    float sc[EPV], sh[EPV];
+                    const bool has_pre = p.pre_scale != nullptr;
+                    if (has_pre && ch_ok) {
+#pragma unroll
+                        for (int e = 0; e < EPV; e += 4) {
+                            float4 a = *reinterpret_cast<const float4*>(p.pre_scale + ch0 + e);
+                            float4 b = *reinterpret_cast<const float4*>(p.pre_shift + ch0 + e);
+                            sc[e] = a.x; sc[e + 1] = a.y; sc[e + 2] = a.z; sc[e + 3] = a.w;
+                            sh[e] = b.x; sh[e + 1] = b.y; sh[e + 2] = b.z; sh[e + 3] = b.w;
+                        }
+                    }
+                    if (MODE == kModeGeneric) {
+                        bool ok[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            int iy = (oyx[i] >> 16) + fr;
+                            int ix = (int)(short)(oyx[i] & 0xFFFF) + fs;
+                            ok[i] = ch_ok && pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                            v[i] = make_uint4(0u, 0u, 0u, 0u);
+                            if (ok[i]) v[i] = LdgNc(in + ((size_t)pix[i] + (size_t)iy * p.W + ix) * p.in_pitch + p.in_coff + ch0);
+                        }
+                        if (has_pre) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (!ok[i]) continue;  // padding stays exactly zero
+                                float f[EPV];
+                                ME::Unpack(v[i], f);
+#pragma unroll
+                                for (int e = 0; e < EPV; ++e) {
+                                    float t = fmaf(f[e], sc[e], sh[e]);
+                                    f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
+                                }
+                                v[i] = ME::Pack(f);
+                            }
+                        }
+                        MbarWait(&empty_bar[stage], phase ^ 1u);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            int row = rbase + 16 * i;
+                            StsV4(a_base + row * kRowBytes + ((sub ^ (row & 7)) << 4), v[i]);
+                        }
+                    } else {  // kModePool2: A row = mean of the 2x2 input pixels after the prologue
+                        MbarWait(&empty_bar[stage], phase ^ 1u);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            uint4 q[4][4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                int ii = half * 4 + i;
+                                bool ok = ch_ok && pix[ii] >= 0;
+                                int iy = (oyx[ii] >> 16), ix = (int)(short)(oyx[ii] & 0xFFFF);
+#pragma unroll
+                                for (int d = 0; d < 4; ++d) {
+                                    q[i][d] = make_uint4(0u, 0u, 0u, 0u);
+                                    if (ok) q[i][d] = LdgNc(in + ((size_t)pix[ii] + (size_t)(iy + (d >> 1)) * p.W + ix + (d & 1)) * p.in_pitch + p.in_coff + ch0);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                int ii = half * 4 + i;
+                                float acc[EPV];
+#pragma unroll
+                                for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+                                if (ch_ok && pix[ii] >= 0) {
+#pragma unroll
+                                    for (int d = 0; d < 4; ++d) {
+                                        float f[EPV];
+                                        ME::Unpack(q[i][d], f);
+#pragma unroll
+                                        for (int e = 0; e < EPV; ++e) {
+                                            float t = has_pre ? fmaf(f[e], sc[e], sh[e]) : f[e];
+                                            acc[e] += p.pre_relu ? fmaxf(t, 0.f) : t;
+                                        }
+                                    }
+#pragma unroll
+                                    for (int e = 0; e < EPV; ++e) acc[e] *= 0.25f;
+                                }
+                                int row = rbase + 16 * ii;
+                                StsV4(a_base + row * kRowBytes + ((sub ^ (row & 7)) << 4), ME::Pack(acc));
+                            }
+                        }
+                    }
+                }
+                FenceProxyAsync();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                MbarArrive(&full_bar[stage]);
+            }
+        }
+    } else if (warp < 12) {
+        // =========================================================== epilogue
+        const int e = warp & 3;  // TMEM lane quarter this warp may access
+        OutT* out = reinterpret_cast<OutT*>(p.out);
+        uint32_t tile_iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+            const uint32_t acc = tile_iter & 1u, acc_phase = (tile_iter >> 1) & 1u;
+            MbarWait(&tmem_full[acc], acc_phase);
+            TcFenceAfter();
+            const int m = m_tile * kTileM + e * 32 + lane;
+            OutT* orow = out + (size_t)m * p.out_pitch + p.out_coff;
+#pragma unroll 1
+            for (int cg = 0; cg < BN / 32; ++cg) {
+                uint32_t r[32];
+                TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN + cg * 32, r);
+                TmemLoadWait();
+                const int co0 = n_tile * BN + cg * 32;
+                if (m < p.M && co0 < p.Cout) {
+                    float f[32];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        int co = co0 + q;
+                        float t = __uint_as_float(r[q]);
+                        if (co < p.Cout) {
+                            t *= p.out_scale[co];
+                            if (p.bias) t += p.bias[co];
+                        }
+                        f[q] = p.post_relu ? fmaxf(t, 0.f) : t;
+                    }
+                    if (sizeof(OutT) == 2) {
+#pragma unroll
+                        for (int q = 0; q < 32; q += 8) {
+                            if (co0 + q < p.Cout) {
+                                uint4 w = MmaElem<__nv_bfloat16>::Pack(f + q);
+                                *reinterpret_cast<uint4*>(orow + co0 + q) = w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; q += 16) {
+                            if (co0 + q < p.Cout) {
+                                uint4 w = MmaElem<__nv_fp8_e4m3>::Pack(f + q);
+                                *reinterpret_cast<uint4*>(orow + co0 + q) = w;
+                            }
+                        }
+                    }
+                }
+            }
+            TcFenceBefore();
+            MbarArrive(&tmem_empty[acc]);
+        }
+    } else if (warp == 12) {
+        // =========================================================== B producer (TMA)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.num_n_tiles;
+                for (int c = 0; c < p.num_chunks; ++c, ++it) {
+                    const int stage = it % NS;
+                    const uint32_t phase = (it / NS) & 1u;
+                    MbarWait(&empty_bar[stage], phase ^ 1u);
+                    MbarArriveExpectTx(&full_bar[stage], BN * kRowBytes);
+                    TmaLoad2D(smem + stage * Cfg::kStageBytes + kATileBytes, &tmap_w, &full_bar[stage], c * ME::kChunk, n_tile * BN);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, BN);
+            uint32_t it = 0, tile_iter = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+                const uint32_t acc = tile_iter & 1u, acc_phase = (tile_iter >> 1) & 1u;
+                MbarWait(&tmem_empty[acc], acc_phase ^ 1u);
+                TcFenceAfter();
+                const uint32_t d_addr = tmem_base + acc * BN;
+                for (int c = 0; c < p.num_chunks; ++c, ++it) {
+                    const int stage = it % NS;
+                    const uint32_t phase = (it / NS) & 1u;
+                    int valid;  // elements of this chunk that carry data
+                    if (MODE == kModeStem) {
+                        valid = (p.R - 2 * c >= 2 ? 2 : 1) * 32;
+                    } else {
+                        int j = c % p.chunks_per_tap;
+                        valid = p.Cin - j * ME::kChunk;
+                        if (valid > ME::kChunk) valid = ME::kChunk;
+                    }
+                    const int ksteps = (valid + ME::kStepK - 1) / ME::kStepK;
+                    MbarWait(&full_bar[stage], phase);
+                    TcFenceAfter();
+                    const uint32_t a_addr = SmemAddr(smem + stage * Cfg::kStageBytes);
+                    const uint64_t a_desc = MakeSmemDesc(a_addr);
+                    const uint64_t b_desc = MakeSmemDesc(a_addr + kATileBytes);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        // +32 bytes per K step inside the 128-byte swizzle row (start-address field is >>4)
+                        UmmaSS<ME::kKind>(d_addr, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
+                                          (c > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    UmmaCommit(&empty_bar[stage]);
+                    if (c == p.num_chunks - 1) UmmaCommit(&tmem_full[acc]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    TcFenceBefore();
+    __syncthreads();
+    if (warp == 13) {
+        TcFenceAfter();
+        TmemDealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+template <typename MmaT, typename OutT, int BN, int MODE>
+cudaError_t Launch(const CUtensorMap& tm, const UParams& p, cudaStream_t stream) {
+    using Cfg = TileCfg<BN>;
+    auto kern = conv_umma_kernel<MmaT, OutT, BN, MODE>;
+    static int sm_count[64] = {0};  // per instantiation and device; the smem opt-in is a per-device attribute
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!sm_count[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count[dev] = n > 0 ? n : 148;
+    }
+    int tiles = p.num_m_tiles * p.num_n_tiles;
+    int grid = tiles < sm_count[dev] ? tiles : sm_count[dev];
+    kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tm, p);
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+template <typename MmaT, typename OutT, int MODE>
+cudaError_t LaunchBN(int bn, const CUtensorMap& tm, const UParams& p, cudaStream_t stream) {
+    switch (bn) {
+        case 32: return Launch<MmaT, OutT, 32, MODE>(tm, p, stream);
+        case 64: return Launch<MmaT, OutT, 64, MODE>(tm, p, stream);
+        case 128: return Launch<MmaT, OutT, 128, MODE>(tm, p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
 int UmmaKChunkElems(DType d) { return d == DType::FP8 ? 128 : 64; }
-int UmmaPaddedCin(int Cin, int, int, DType d) { int kc = UmmaKChunkElems(d); return (Cin + kc - 1) / kc * kc; }
-bool UmmaSupported(const ConvArgs&) { return false; }
-cudaError_t ConvUmma(const ConvArgs&, const UmmaWeights&, cudaStream_t) { return cudaErrorNotSupported; }
-}}
+
+int UmmaPaddedCin(int Cin, int, int, DType d) {
+    int kc = UmmaKChunkElems(d);
+    return (Cin + kc - 1) / kc * kc;
+}
+
+bool UmmaSupported(const ConvArgs& a) {
+    const DType it = a.in.dtype, ot = a.out.dtype;
+    if (it != DType::BF16 && it != DType::FP8) return false;
+    if (ot != DType::BF16 && ot != DType::FP8) return false;
+    if (it == DType::FP8 && ot != DType::FP8) return false;
+    const int esz_in = (int)DTypeSize(it), esz_out = (int)DTypeSize(ot);
+    if (a.Cout % 8 != 0 || (a.out.pitch * esz_out) % 16 != 0 || (a.out.c_off * esz_out) % 16 != 0) return false;
+    if (a.Cin < 16) {  // stem: bf16 NHWC4, 7 rows x (8 pixels x 4 channels)
+        return it == DType::BF16 && a.in.pitch == 4 && a.in.c_off == 0 && a.S <= 7 && a.R <= 8 && !a.pool2 && !a.pre_scale;
+    }
+    const int step = it == DType::BF16 ? 16 : 32;
+    if (a.Cin % step != 0) return false;
+    if ((a.in.pitch * esz_in) % 16 != 0 || (a.in.c_off * esz_in) % 16 != 0) return false;
+    if (a.pool2 && !(a.R == 1 && a.S == 1 && a.in.H % 2 == 0 && a.in.W % 2 == 0)) return false;
+    return true;
+}
+
+cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream) {
+    if (!UmmaSupported(a) || !w.tensor_map) return cudaErrorInvalidValue;
+    const DType it = a.in.dtype, ot = a.out.dtype;
+    const bool stem = a.Cin < 16;
+    const int kc = UmmaKChunkElems(it);
+    UParams p;
+    p.in = a.in.base; p.out = a.out.base;
+    p.pre_scale = a.pre_scale; p.pre_shift = a.pre_shift; p.out_scale = w.out_scale; p.bias = a.bias;
+    p.pre_relu = a.pre_relu; p.post_relu = a.post_relu;
+    p.H = a.in.H; p.W = a.in.W; p.in_pitch = a.in.pitch; p.in_coff = a.in.c_off;
+    p.Ho = a.out.H; p.Wo = a.out.W; p.out_pitch = a.out.pitch; p.out_coff = a.out.c_off; p.Cout = a.Cout;
+    p.Cin = a.Cin; p.R = a.R; p.S = a.S; p.stride = a.stride; p.pad = a.pad;
+    p.M = a.n * p.Ho * p.Wo;
+    if (p.M <= 0) return cudaSuccess;
+    const int bn = a.Cout <= 32 ? 32 : a.Cout <= 64 ? 64 : 128;
+    p.num_m_tiles = (p.M + kTileM - 1) / kTileM;
+    p.num_n_tiles = w.Cout_pad / bn;
+    p.chunks_per_tap = stem ? 1 : (a.Cin + kc - 1) / kc;
+    p.num_chunks = stem ? w.K_pad / kc : a.R * a.S * p.chunks_per_tap;
+    const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(w.tensor_map);
+    if (stem) {
+        if (ot == DType::BF16) return LaunchBN<__nv_bfloat16, __nv_bfloat16, kModeStem>(bn, tm, p, stream);
+        return LaunchBN<__nv_bfloat16, __nv_fp8_e4m3, kModeStem>(bn, tm, p, stream);
+    }
+    if (it == DType::BF16) {
+        if (ot == DType::BF16)
+            return a.pool2 ? LaunchBN<__nv_bfloat16, __nv_bfloat16, kModePool2>(bn, tm, p, stream)
+                           : LaunchBN<__nv_bfloat16, __nv_bfloat16, kModeGeneric>(bn, tm, p, stream);
+        return cudaErrorInvalidValue;
+    }
+    return a.pool2 ? LaunchBN<__nv_fp8_e4m3, __nv_fp8_e4m3, kModePool2>(bn, tm, p, stream)
+                   : LaunchBN<__nv_fp8_e4m3, __nv_fp8_e4m3, kModeGeneric>(bn, tm, p, stream);
+}
+
+}  // namespace kernels
+}  // namespace b200

@@ -821,7 +821,9 @@ private:
         const char* no_reuse = getenv("B200_ENGINE_NO_REUSE");  // debugging: keep every intermediate value alive
         for (auto& b : plan_.buffers) {
             if (no_reuse && no_reuse[0] == '1') { b.first_step = -1; b.last_step = nsteps; }
-            if (b.role == BufferDesc::Role::Input) b.first_step = -1;
+            // graph inputs stay resident for the whole forward so a staged batch can be re-run (device-resident
+            // benchmarking); graph outputs stay until the D2H copy
+            if (b.role == BufferDesc::Role::Input) { b.first_step = -1; b.last_step = nsteps; }
             if (b.role == BufferDesc::Role::Output) b.last_step = nsteps;
             if (b.last_step < 0) { b.first_step = -1; b.last_step = nsteps; }  // untouched (pass-through)
             if (b.role == BufferDesc::Role::Input && b.last_step < 0) b.last_step = nsteps;

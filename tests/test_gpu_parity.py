@@ -1,0 +1,293 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C-ABI exactly as the
+reference's Go binding would call it, against the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star): FP32 logits within 1e-3 relative (to max|logit|) with identical top-1; BF16/FP8
+"top-5 agreement" >= 99 % on the fixed synthetic set, defined as: the oracle's top-1 class is among the
+engine's top-5 (both the set-overlap and top-1 agreement are reported and loosely gated as well)."""
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from oracle.onnx_oracle import OnnxOracle
+from tools import onnx_lite, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(autouse=True)
+def _one_gpu_small_arena(monkeypatch):
+    monkeypatch.setenv("B200_ENGINE_DEVICES", os.environ.get("B200_TEST_DEVICES", "0"))
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "32")
+    monkeypatch.delenv("B200_ENGINE_PRECISION", raising=False)
+
+
+def _serve(pkg, repo, name, feeds, out_shapes, precision, monkeypatch, max_batch=None):
+    monkeypatch.setenv("B200_ENGINE_PRECISION", precision)
+    if max_batch:
+        monkeypatch.setenv("B200_ENGINE_MAX_BATCH", str(max_batch))
+    mgr = pkg.InferenceManager(repo)
+    try:
+        mgr.load_model(name)
+        outs = mgr.run_inference(name, "", [pkg.TensorData(k, v) for k, v in feeds.items()],
+                                 [pkg.OutputConfig(k, list(s)) for k, s in out_shapes.items()])
+        mgr.unload_model(name)
+        return [o.data for o in outs]
+    finally:
+        mgr.shutdown()
+
+
+def _graph_case(tmp_path, name, nodes, inits, in_shape, out_name, out_shape):
+    g = onnx_lite.Graph(name=name)
+    g.nodes = nodes
+    g.initializers = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in inits.items()}
+    g.inputs = [onnx_lite.ValueInfo("x", onnx_lite.FLOAT, ["N"] + list(in_shape))]
+    g.outputs = [onnx_lite.ValueInfo(out_name, onnx_lite.FLOAT, ["N"] + list(out_shape))]
+    d = tmp_path / name / "1"
+    os.makedirs(d, exist_ok=True)
+    path = str(d / "model.onnx")
+    onnx_lite.save(onnx_lite.Model(g, ir_version=7, opset=12), path)
+    return path
+
+
+def _bn(rng, c, prefix):
+    return {prefix + ".g": rng.uniform(0.5, 1.5, c), prefix + ".b": rng.normal(0, 0.2, c),
+            prefix + ".m": rng.normal(0, 0.3, c), prefix + ".v": rng.uniform(0.5, 1.5, c)}
+
+
+def _bn_node(x, prefix, out):
+    return onnx_lite.Node("BatchNormalization", [x, prefix + ".g", prefix + ".b", prefix + ".m", prefix + ".v"], [out],
+                          {"epsilon": 1e-5})
+
+
+def _conv_node(x, w, out, k, s=1, p=0, bias=None):
+    return onnx_lite.Node("Conv", [x, w] + ([bias] if bias else []), [out],
+                          {"kernel_shape": [k, k], "strides": [s, s], "pads": [p, p, p, p], "dilations": [1, 1], "group": 1})
+
+
+CASES = ["conv1x1_bn_relu", "conv1x1_partial_chunk", "conv3x3", "stem_maxpool", "transition", "dense_block", "cout256",
+         "gap_gemm_softmax"]
+TOL = {"fp32": 2e-5, "bf16": 2.5e-2, "fp8": 1.5e-1}
+
+
+def _build_case(case, tmp_path, rng):
+    """returns (model_path, model_name, input array [N,C,H,W], output value name)"""
+    k = lambda *s: rng.normal(0, 1.0, s) / np.sqrt(np.prod(s[1:]))  # noqa: E731
+    if case == "conv1x1_bn_relu":
+        inits = {**_bn(rng, 64, "bn"), "w": k(128, 64, 1, 1), "b": rng.normal(0, 0.1, 128)}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1, bias="b"),
+                 onnx_lite.Node("Relu", ["c"], ["y"])]
+        shp, out = (64, 12, 12), (128, 12, 12)
+    elif case == "conv1x1_partial_chunk":
+        inits = {**_bn(rng, 96, "bn"), "w": k(128, 96, 1, 1)}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "y", 1)]
+        shp, out = (96, 7, 7), (128, 7, 7)
+    elif case == "conv3x3":
+        inits = {"w": k(32, 128, 3, 3)}
+        nodes = [_conv_node("x", "w", "y", 3, 1, 1)]
+        shp, out = (128, 14, 14), (32, 14, 14)
+    elif case == "stem_maxpool":
+        inits = {"w": k(64, 3, 7, 7), "b": rng.normal(0, 0.1, 64)}
+        nodes = [_conv_node("x", "w", "c", 7, 2, 3, bias="b"), onnx_lite.Node("Relu", ["c"], ["r"]),
+                 onnx_lite.Node("MaxPool", ["r"], ["y"], {"kernel_shape": [3, 3], "strides": [2, 2], "pads": [1, 1, 1, 1]})]
+        shp, out = (3, 40, 40), (64, 10, 10)
+    elif case == "transition":
+        inits = {**_bn(rng, 128, "bn"), "w": k(64, 128, 1, 1)}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1),
+                 onnx_lite.Node("AveragePool", ["c"], ["y"], {"kernel_shape": [2, 2], "strides": [2, 2], "pads": [0, 0, 0, 0]})]
+        shp, out = (128, 12, 12), (64, 6, 6)
+    elif case == "dense_block":
+        inits, nodes, feats = {}, [], ["x"]
+        c = 64
+        for li in range(3):
+            cat = f"cat{li}"
+            nodes.append(onnx_lite.Node("Concat", list(feats), [cat], {"axis": 1}))
+            inits.update(_bn(rng, c, f"bn{li}"))
+            inits[f"w1_{li}"] = k(128, c, 1, 1)
+            inits[f"b1_{li}"] = rng.normal(0, 0.1, 128)
+            inits[f"w2_{li}"] = k(32, 128, 3, 3)
+            nodes += [_bn_node(cat, f"bn{li}", f"n{li}"), onnx_lite.Node("Relu", [f"n{li}"], [f"r{li}"]),
+                      _conv_node(f"r{li}", f"w1_{li}", f"c1_{li}", 1, bias=f"b1_{li}"),
+                      onnx_lite.Node("Relu", [f"c1_{li}"], [f"r2_{li}"]), _conv_node(f"r2_{li}", f"w2_{li}", f"f{li}", 3, 1, 1)]
+            feats.append(f"f{li}")
+            c += 32
+        nodes.append(onnx_lite.Node("Concat", list(feats), ["y"], {"axis": 1}))
+        shp, out = (64, 9, 9), (160, 9, 9)
+    elif case == "cout256":
+        inits = {"w": k(256, 128, 1, 1)}
+        nodes = [_conv_node("x", "w", "y", 1)]
+        shp, out = (128, 10, 10), (256, 10, 10)
+    elif case == "gap_gemm_softmax":
+        inits = {**_bn(rng, 64, "bn"), "w": rng.normal(0, 0.2, (10, 64)), "b": rng.normal(0, 0.1, 10)}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), onnx_lite.Node("GlobalAveragePool", ["r"], ["g"]),
+                 onnx_lite.Node("Flatten", ["g"], ["f"], {"axis": 1}),
+                 onnx_lite.Node("Gemm", ["f", "w", "b"], ["l"], {"transB": 1, "alpha": 1.0, "beta": 1.0}),
+                 onnx_lite.Node("Softmax", ["l"], ["y"], {"axis": 1})]
+        shp, out = (64, 7, 7), (10,)
+    else:
+        raise KeyError(case)
+    path = _graph_case(tmp_path, case, nodes, inits, shp, "y", out)
+    return path, case, shp, out
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp8"])
+@pytest.mark.parametrize("case", CASES)
+def test_operator_graphs_match_oracle(pkg, tmp_path, monkeypatch, case, precision):
+    rng = np.random.default_rng(abs(hash(case)) % 2**31)
+    path, name, shp, out = _build_case(case, tmp_path, rng)
+    n = 5
+    x = rng.uniform(0, 1, (n,) + tuple(shp)).astype(np.float32) if shp[0] == 3 else rng.normal(0, 1, (n,) + tuple(shp)).astype(np.float32)
+    want = OnnxOracle(path).run({"x": x})[0]
+    got = _serve(pkg, str(tmp_path), name, {"x": x}, {"y": (n,) + tuple(out)}, precision, monkeypatch)[0]
+    assert got.shape == want.shape
+    err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)
+    assert np.isfinite(got).all() and err < TOL[precision], f"{case}/{precision}: rel err {err:.3e}"
+
+
+def test_test_model_known_answers_through_the_c_abi(pkg, repo_dir, monkeypatch):
+    with open(os.path.join(ROOT, "tests", "golden", "test_model_kat.json")) as fh:
+        vectors = json.load(fh)["vectors"]
+    for precision in ("fp32", "bf16", "fp8"):  # rank-2 graphs always run in fp32, whatever the mode
+        for v in vectors:
+            x = np.asarray(v["input"], np.float32)
+            y = _serve(pkg, repo_dir, "test_model", {"input": x}, {"output": (1, 2)}, precision, monkeypatch)[0]
+            np.testing.assert_allclose(y, np.asarray(v["output"], np.float32), rtol=2e-6, atol=1e-6)
+    # batch > the batch baked into the file is accepted (documented deviation)
+    xs = np.random.default_rng(0).normal(0, 1, (7, 3)).astype(np.float32)
+    y = _serve(pkg, repo_dir, "test_model", {"input": xs}, {"output": (7, 2)}, "fp32", monkeypatch)[0]
+    want = OnnxOracle(os.path.join(repo_dir, "test_model", "1", "model.onnx")).run_numpy({"input": xs})[0]
+    np.testing.assert_allclose(y, want, rtol=1e-5, atol=1e-6)
+
+
+def _agreement(ref, got):
+    r5, g5 = np.argsort(-ref, 1)[:, :5], np.argsort(-got, 1)[:, :5]
+    return {"top1": float(np.mean(ref.argmax(1) == got.argmax(1))),
+            "ref_top1_in_top5": float(np.mean([r in g for r, g in zip(ref.argmax(1), g5)])),
+            "top5_overlap": float(np.mean([len(set(a) & set(b)) / 5 for a, b in zip(r5, g5)])),
+            "max_rel": float(np.abs(ref - got).max() / np.abs(ref).max())}
+
+
+def test_densenet_fp32_matches_golden_logits(pkg, repo_dir, monkeypatch):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "densenet_logits.npz"))
+    n = int(g["n"])
+    x = synth.to_model_input(synth.synthetic_images_u8(n, start=int(g["start"])))
+    got = _serve(pkg, repo_dir, "densenet_onnx", {"data_0": x}, {"fc6_1": (n, 1000)}, "fp32", monkeypatch)[0]
+    a = _agreement(g["logits_fp64"], got)
+    assert a["max_rel"] < 1e-3 and a["top1"] == 1.0, a          # north_star fp32 gate
+    assert _agreement(g["logits_fp32"], got)["max_rel"] < 1e-4   # in practice fp32-reassociation noise only
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp8"])
+def test_densenet_low_precision_top5_agreement(pkg, repo_dir, densenet_path, monkeypatch, precision):
+    n = 96
+    x = synth.to_model_input(synth.synthetic_images_u8(n, start=2000))
+    ref = OnnxOracle(densenet_path).run({"data_0": x})[0]
+    got = _serve(pkg, repo_dir, "densenet_onnx", {"data_0": x}, {"fc6_1": (n, 1000)}, precision, monkeypatch, max_batch=96)[0]
+    a = _agreement(ref, got)
+    print(precision, a)
+    assert np.isfinite(got).all()
+    assert a["ref_top1_in_top5"] >= 0.99, a
+    assert a["top5_overlap"] >= (0.9 if precision == "bf16" else 0.75), a
+    assert a["max_rel"] < (0.05 if precision == "bf16" else 0.3), a
+
+
+def test_batch_properties_and_chunking(pkg, repo_dir, monkeypatch):
+    """Size-independent properties: per-image results do not depend on batch composition, batch order,
+    or on how the batch is chunked through the arena (max_batch 4 < n)."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "fp32")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "4")
+    x = synth.to_model_input(synth.synthetic_images_u8(10, start=3000))
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        run = lambda a: mgr.run_inference("densenet_onnx", "", [pkg.TensorData("data_0", a)],  # noqa: E731
+                                          [pkg.OutputConfig("fc6_1", [len(a), 1000])])[0].data
+        full = run(x)                                   # 10 images through a 4-image arena: 3 chunks
+        one = np.concatenate([run(x[i:i + 1]) for i in range(10)])
+        perm = np.random.default_rng(1).permutation(10)
+        assert np.abs(full - one).max() / np.abs(full).max() < 1e-5
+        assert np.abs(run(x[perm]) - full[perm]).max() / np.abs(full).max() < 1e-5
+        st = mgr.get_model("densenet_onnx").get_stats()
+        assert st.inference_count == 12 and st.memory_usage_bytes > 30e6 and st.last_inference_time_ns > 0
+        md = mgr.get_model("densenet_onnx").get_metadata()
+        assert md.inputs == ["data_0"] and md.outputs == ["fc6_1"]      # names adopted from the graph
+        # Go allocates the output from config.json's [1,1000,1,1]: rank-4 dims buffer, 4000 bytes
+        m = mgr.get_model("densenet_onnx")
+        y = m.infer([pkg.TensorData("data_0", x[:1])], [pkg.OutputConfig("fc6_1", [1, 1000, 1, 1])])[0].data
+        assert np.abs(y.reshape(1, 1000) - full[:1]).max() / np.abs(full).max() < 1e-5
+        assert m.last_returned_shapes == [[1, 1000]]
+    finally:
+        mgr.shutdown()
+
+
+def test_validation_errors_match_reference_messages(pkg, repo_dir, monkeypatch):
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "fp32")
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("test_model")
+        with pytest.raises(pkg.EngineError, match="^Model already loaded$"):
+            mgr.load_model("test_model")
+        m = mgr.get_model("test_model")
+        ok = np.zeros((1, 3), np.float32)
+        with pytest.raises(pkg.EngineError, match="Unexpected input name: data"):
+            m.infer([pkg.TensorData("data", ok)], [pkg.OutputConfig("output", [1, 2])])
+        with pytest.raises(pkg.EngineError, match="Expected 1 inputs, got 2"):
+            m.infer([pkg.TensorData("input", ok), pkg.TensorData("input", ok)], [pkg.OutputConfig("output", [1, 2])])
+        with pytest.raises(pkg.EngineError, match="Input shape mismatch for input at dimension 1"):
+            m.infer([pkg.TensorData("input", np.zeros((1, 4), np.float32))], [pkg.OutputConfig("output", [1, 2])])
+        with pytest.raises(pkg.EngineError, match="Input shape mismatch for input: expected 2 dimensions, got 3"):
+            m.infer([pkg.TensorData("input", np.zeros((1, 3, 1), np.float32))], [pkg.OutputConfig("output", [1, 2])])
+        with pytest.raises(pkg.EngineError, match="Input data type mismatch for input"):
+            m.infer([pkg.TensorData("input", np.zeros((1, 3), np.int32), pkg.DataType.INT32)], [pkg.OutputConfig("output", [1, 2])])
+        # output buffer smaller than the result: min(data_size, produced) bytes are written, no overflow
+        y = m.infer([pkg.TensorData("input", np.ones((1, 3), np.float32))], [pkg.OutputConfig("output", [1, 1])])[0].data
+        np.testing.assert_allclose(y, [[-1.6748662]], rtol=2e-6)
+        # unload while a wrapper is still held: the wrapper must stay safe to use and destroy
+        mgr.unload_model("test_model")
+        assert not m.is_loaded()
+        with pytest.raises(pkg.EngineError, match="Model not loaded"):
+            m.infer([pkg.TensorData("input", ok)], [pkg.OutputConfig("output", [1, 2])])
+    finally:
+        mgr.shutdown()
+
+
+def test_concurrent_callers_on_one_handle(pkg, repo_dir, monkeypatch):
+    """gin serves each request on its own goroutine/OS thread: ModelInfer must be re-entrant."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "fp32")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "8")
+    x = synth.to_model_input(synth.synthetic_images_u8(8, start=4000))
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        want = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [8, 1000])])[0].data
+        errs = []
+
+        def worker(i):
+            try:
+                for _ in range(3):
+                    y = m.infer([pkg.TensorData("data_0", x[i:i + 1])], [pkg.OutputConfig("fc6_1", [1, 1000])])[0].data
+                    if np.abs(y - want[i:i + 1]).max() / np.abs(want).max() > 1e-5:
+                        errs.append((i, "mismatch"))
+            except Exception as e:  # noqa: BLE001
+                errs.append((i, repr(e)))
+
+        ts = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs
+        assert m.get_stats().inference_count == 1 + 24
+    finally:
+        mgr.shutdown()
+
+
+def test_device_queries_and_vector_add(pkg):
+    assert pkg.is_cuda_available() and pkg.get_device_count() >= 1
+    info = pkg.get_device_info(0)
+    assert info.startswith("Device 0: ") and "(Compute Capability 10." in info
+    mem = pkg.get_memory_info(0)
+    assert mem.total > 100e9 and mem.free <= mem.total and mem.used == mem.total - mem.free
+    assert pkg.kernel_launch_count() >= 0
