@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""bench.py — DenseNet-121 img/s through the B200-native engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp8|bf16|fp32] [--batch 256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU)
+    python bench.py --impl reference ...      (the reference's CPU path: oracle graph interpreter on host cores)
+
+A "step" is one forward pass of one batch (default 256 images, 3x224x224, synthetic) per GPU.
+  value      whole-job img/s with the batch already resident in HBM (device events on the engine's stream)
+  e2e        same metric through the reference-facing C-ABI call `ModelInfer` with pinned HOST buffers
+             (H2D of the fp32 NCHW input and D2H of the logits inside the timed region)
+  roofline   the dominant kernel family (the tcgen05 implicit-GEMM conv kernel, 120 launches per forward):
+             algorithmic HBM bytes / device time against the measured HBM peak (+ tensor fraction alongside)
+  cpu_baseline  the CPU oracle ("torch-CPU stand-in for ORT-CPU 1.21.0") on a bounded sample, same box
+Scaling is weak: every rank/GPU processes its own `--batch` images; no collective is on the data path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "densenet121_images_per_second"
+UNIT = "img/s"
+FLOPS_PER_IMAGE = 5.668e9
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist():
+    """(rank, local_rank, world) and a MAX-reduce / barrier pair; torch.distributed only under torchrun."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 0, 1, (lambda v: v), (lambda: None)
+    import torch
+    import torch.distributed as dist
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", os.environ["RANK"]))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def reduce_max(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    return rank, local, world, reduce_max, barrier
+
+
+def cpu_oracle_throughput(n_images: int, batch: int, threads: int | None = None):
+    """img/s of the CPU oracle on a bounded sample of the bench workload (same model file, same inputs)."""
+    import torch
+    from oracle.onnx_oracle import OnnxOracle
+    from tools import synth
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    o = OnnxOracle(os.path.join(ROOT, "models", "densenet_onnx", "1", "model.onnx"))
+    x = synth.to_model_input(synth.synthetic_images_u8(min(batch, n_images), start=0))
+    o.run({"data_0": x[:2]})  # warm-up (thread pools, primitive caches)
+    done, t0 = 0, time.perf_counter()
+    while done < n_images:
+        o.run({"data_0": x})
+        done += len(x)
+    dt = time.perf_counter() - t0
+    return done / dt, cores, done, dt
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path: ONNX Runtime cannot be installed here (no wheel,
+    no network), so this is the oracle port — a graph interpreter of the same .onnx on torch-CPU kernels,
+    all host threads.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as ge
+    ge.ensure_fixtures()
+    sample = 16  # images per step: a bounded sample of the 256-image batch
+    for _ in range(args.warmup):
+        cpu_oracle_throughput(sample, sample)
+    per = []
+    cores = 0
+    for _ in range(args.steps):
+        ips, cores, done, dt = cpu_oracle_throughput(sample, sample)
+        per.append(dt)
+    value = sample * len(per) / sum(per)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(per) / len(per), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"DenseNet-121 3x224x224 fp32 forward, bounded sample of {sample} images per step "
+                                   f"(of the {args.batch}-image batch)", "batch": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} images/step x {args.steps} steps; torch-CPU stand-in for ORT-CPU 1.21.0"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("B200_BENCH_PRECISION", "fp8"), choices=["fp32", "bf16", "fp8"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, local, world, reduce_max, barrier = _dist()
+    in_process_multi = world == 1 and args.gpus > 1
+    os.environ["B200_ENGINE_PRECISION"] = args.precision
+    os.environ["B200_ENGINE_MAX_BATCH"] = str(args.batch)
+    os.environ["B200_ENGINE_DEVICES"] = ",".join(str(i) for i in range(args.gpus)) if in_process_multi else str(local)
+
+    import numpy as np
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    if rank == 0:
+        ge.ensure_fixtures()
+    barrier()
+    ge.ensure_fixtures()
+    from tools import synth
+
+    if not pkg.is_cuda_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    mgr = pkg.InferenceManager(os.path.join(ROOT, "models"))
+    mgr.load_model("densenet_onnx")
+    model = mgr.get_model("densenet_onnx")
+    B = args.batch
+    base = synth.to_model_input(synth.synthetic_images_u8(min(B, 32), start=rank * 32))
+    x = np.concatenate([base] * ((B + len(base) - 1) // len(base)))[:B]
+
+    # pinned host buffers for the end-to-end leg
+    import torch
+    x_pinned_t = torch.from_numpy(x).pin_memory()
+    x_pinned = x_pinned_t.numpy()
+    inp = pkg.TensorData("data_0", x_pinned)
+    outc = [pkg.OutputConfig("fc6_1", [B, 1000])]
+
+    # ---------------- device-resident leg ----------------
+    model.stage_input(inp)
+    model.forward_device(B, args.warmup, True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = pkg.kernel_launch_count()
+    t_wall0 = time.perf_counter()
+    ms = model.forward_device(B, args.steps, True)  # CUDA events on the engine's stream, L2 flushed between steps
+    t_wall = time.perf_counter() - t_wall0
+    launches = pkg.kernel_launch_count() - launches0
+    barrier()
+    clocks = sampler.stop()
+    total_ms = reduce_max(float(ms.sum()))
+    n_gpus = args.gpus
+    images = B * args.steps * n_gpus
+    value = images / (total_ms * 1e-3)
+    logits = model.read_output(B * 1000).reshape(B, 1000)
+    assert np.isfinite(logits).all()
+
+    # ---------------- end-to-end leg (host buffers through ModelInfer) ----------------
+    for _ in range(2):
+        model.infer([inp], outc)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        out = model.infer([inp], outc)[0].data
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    barrier()
+    e2e_value = B * e2e_steps * n_gpus / e2e_s if not in_process_multi else B * e2e_steps / e2e_s
+    e2e_rel = float(np.abs(out - logits).max() / np.abs(logits).max())
+
+    line = None
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel family (per-step device events) ----------------
+        peaks = _peaks()
+        prof = model.profile_steps(B, 2)
+        conv = [p for p in prof if p["kind"] == "conv" and p.get("umma")] or [p for p in prof if p["kind"] == "conv"]
+        conv_ms = sum(p["ms"] for p in conv)
+        all_ms = sum(p["ms"] for p in prof)
+        conv_bytes = sum(p["bytes"] for p in conv)
+        conv_flops = sum(p["flops"] for p in conv)
+        gbs = conv_bytes / (conv_ms * 1e-3) / 1e9
+        tfl = conv_flops / (conv_ms * 1e-3) / 1e12
+        tensor_peak = peaks["bf16_tflops_sustained"] * (2.0 if args.precision == "fp8" else 1.0 if args.precision == "bf16" else 0.5)
+        roofline = {"bound": "hbm", "kernel": "conv_umma_kernel (tcgen05 implicit GEMM)" if conv and conv[0].get("umma") else "conv_simt_f32_kernel",
+                    "launches_per_step": len(conv), "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "share_of_step": conv_ms / all_ms if all_ms else None,
+                    "tensor": {"achieved_tflops": tfl, "peak_tflops": tensor_peak, "frac": tfl / tensor_peak,
+                               "peak_note": "sustained measured bf16 cuBLAS x2 for fp8 / x0.5 for tf32-class; no fp8 peak was measured"},
+                    "algorithmic_bytes_per_image": conv_bytes / B, "algorithmic_flops_per_image": conv_flops / B}
+        # bs1 latency (p50) for the same precision, device + e2e
+        lat = {}
+        try:
+            one = pkg.TensorData("data_0", x_pinned[:1])
+            model.stage_input(one)
+            l_ms = model.forward_device(1, 200, False)[20:]
+            t = []
+            for i in range(120):
+                t0 = time.perf_counter()
+                model.infer([one], [pkg.OutputConfig("fc6_1", [1, 1000])])
+                t.append(time.perf_counter() - t0)
+            lat = {"bs1_p50_ms_device": float(np.median(l_ms)), "bs1_p50_ms_e2e": float(np.median(t[20:]) * 1e3)}
+        except Exception as e:  # noqa: BLE001
+            lat = {"error": repr(e)}
+        cpu = None
+        if not args.no_cpu_baseline:
+            ips, cores, done, dt = cpu_oracle_throughput(96, 32)
+            cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{done} images of the same workload in {dt:.1f}s; oracle graph interpreter on torch-CPU "
+                             f"(stand-in for ORT-CPU 1.21.0, which cannot be installed here)"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp8": "fp8-e4m3 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)", "fp32": "f32"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": f"DenseNet-121 3x224x224 forward, batch {B} per GPU, {args.precision} "
+                                       f"(BASELINE.json configs[3])", "batch_per_gpu": B, "global_batch": B * n_gpus,
+                           "precision": args.precision, "parallelism": f"dp{n_gpus} (replicated weights, no collective)",
+                           "launch": "torchrun one rank per GPU" if world > 1 else ("in-process replicas" if in_process_multi else "single process"),
+                           "l2": "L2 flushed (256 MiB write) before every timed step; activation arena > L2"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(B * 1000 * 4),
+                        "steps": e2e_steps, "api": "ModelInfer (C-ABI) with pinned host buffers", "max_rel_vs_device_leg": e2e_rel},
+                "roofline": roofline, "cpu_baseline": cpu, "latency": lat,
+                "wall_clock_check_ms_per_step": 1e3 * t_wall / args.steps}
+    mgr.shutdown()
+    barrier()
+    if line is not None:
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -24,6 +24,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace b200 {
@@ -229,16 +231,80 @@ struct UParams {
     int M;
     int num_m_tiles, num_n_tiles;
     int chunks_per_tap, num_chunks;
+    int cin_pad, cout_pad;
 };
 
-enum : int { kModeGeneric = 0, kModePool2 = 1, kModeStem = 2 };
+// A-producer flavours
+enum : int {
+    kModeLinear = 0,     // 1x1, stride 1, no padding: input pixel == output pixel; register path, optional prologue
+    kModeGather = 1,     // RxS window with zero padding, no prologue: cp.async (LDGSTS) with zero fill, deep pipeline
+    kModeGatherPre = 2,  // RxS window WITH prologue (not used by DenseNet): register path
+    kModePool2 = 3,      // 1x1 on the 2x2 average of the prologue-transformed input (transition layers)
+    kModeStem = 4        // 7x7/s2 on a 3(+1 pad)-channel image: 8-byte cp.async, 8 pixels x 4 channels per filter row
+};
+
+constexpr int kMaxCin = 2048;       // prologue vectors staged in shared memory
+constexpr int kMaxCoutPad = 1024;   // epilogue vectors staged in shared memory
+constexpr int kVecSmemBytes = (2 * kMaxCin + 2 * kMaxCoutPad) * 4;
 
 template <int BN> struct TileCfg {
     static constexpr int kStageBytes = kATileBytes + BN * kRowBytes;
     static constexpr int kStages = BN == 128 ? 6 : 8;
     static constexpr int kTmemCols = BN == 128 ? 256 : BN == 64 ? 128 : 64;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kVecSmemBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+__device__ __forceinline__ void CpAsync16(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void CpAsync8(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void CpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Walks the (tile, K-chunk) sequence of this CTA, visiting every second chunk (one producer group's share).
+struct ChunkIter {
+    int tile, c;
+    uint32_t it;
+    __device__ __forceinline__ void Init(int group, int num_chunks) {
+        tile = blockIdx.x;
+        c = 0;
+        it = 0;
+        if (group) Step(1, num_chunks);
+    }
+    __device__ __forceinline__ void Step(int n, int num_chunks) {
+        c += n;
+        it += n;
+        while (c >= num_chunks) {
+            c -= num_chunks;
+            tile += gridDim.x;
+        }
+    }
+};
+
+struct RowInfo {
+    int pix[8];  // img * H * W, or -1 for rows past M
+    int oyx[8];  // (iy0 << 16) | (ix0 & 0xFFFF): top-left input coordinate of the receptive field
+};
+
+template <int MODE>
+__device__ __forceinline__ void DecodeRows(const UParams& p, int m_tile, int rbase, RowInfo& ri) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m_tile * kTileM + rbase + 16 * i;
+        if (m < p.M) {
+            int ox = m % p.Wo, oy = (m / p.Wo) % p.Ho, img = m / (p.Wo * p.Ho);
+            int iy0 = (MODE == kModePool2) ? oy * 2 : oy * p.stride - p.pad;
+            int ix0 = (MODE == kModePool2) ? ox * 2 : ox * p.stride - p.pad;
+            ri.pix[i] = img * p.H * p.W;
+            ri.oyx[i] = (int)(((unsigned)iy0 << 16) | ((unsigned)ix0 & 0xFFFFu));
+        } else {
+            ri.pix[i] = -1;
+            ri.oyx[i] = 0;
+        }
+    }
+}
 
 // ------------------------------------------------------------------ the kernel
 template <typename MmaT, typename OutT, int BN, int MODE>
@@ -250,7 +316,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + NS * Cfg::kStageBytes);
+    float* s_pre_scale = reinterpret_cast<float*>(smem + NS * Cfg::kStageBytes);
+    float* s_pre_shift = s_pre_scale + kMaxCin;
+    float* s_out_scale = s_pre_shift + kMaxCin;
+    float* s_bias = s_out_scale + kMaxCoutPad;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + kMaxCoutPad);
     uint64_t* empty_bar = full_bar + NS;
     uint64_t* tmem_full = empty_bar + NS;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -273,6 +343,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         PrefetchTensorMap(&tmap_w);
     }
     if (warp == 13) TmemAlloc(tmem_slot, Cfg::kTmemCols);
+    // per-channel vectors -> shared memory (read as broadcasts by the producers / the epilogue)
+    if (p.pre_scale) {
+        for (int i = threadIdx.x; i < p.cin_pad; i += kThreads) {
+            s_pre_scale[i] = i < p.Cin ? p.pre_scale[i] : 0.f;
+            s_pre_shift[i] = i < p.Cin ? p.pre_shift[i] : 0.f;
+        }
+    }
+    for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
+        s_out_scale[i] = i < p.Cout ? p.out_scale[i] : 0.f;
+        s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+    }
     TcFenceBefore();
     __syncthreads();
     TcFenceAfter();
@@ -285,145 +366,229 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const int sub = pt & 7;     // which 16-byte piece of the 128-byte row
         const int rbase = pt >> 3;  // rows rbase + 16*i
         const MmaT* in = reinterpret_cast<const MmaT*>(p.in);
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.num_n_tiles;
-            int pix[8];   // input pixel index of tap (0,0) before padding offset, or -1 for rows past M
-            int oyx[8];   // (iy0 << 16) | (ix0 & 0xFFFF): top-left input coordinate of the receptive field
+        const bool has_pre = p.pre_scale != nullptr;
+        uint32_t sw_off[8];         // swizzled byte offset of this thread's piece in each of its 8 rows
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int m = m_tile * kTileM + rbase + 16 * i;
-                if (m < p.M) {
-                    int ox = m % p.Wo, oy = (m / p.Wo) % p.Ho, img = m / (p.Wo * p.Ho);
-                    int iy0 = (MODE == kModePool2) ? oy * 2 : oy * p.stride - p.pad;
-                    int ix0 = (MODE == kModePool2) ? ox * 2 : ox * p.stride - p.pad;
-                    pix[i] = img * p.H * p.W;
-                    oyx[i] = (int)(((unsigned)iy0 << 16) | ((unsigned)ix0 & 0xFFFFu));
-                } else {
-                    pix[i] = -1;
-                    oyx[i] = 0;
+        for (int i = 0; i < 8; ++i) {
+            int row = rbase + 16 * i;
+            sw_off[i] = row * kRowBytes + ((sub ^ (row & 7)) << 4);
+        }
+        ChunkIter cur;
+        cur.Init(group, p.num_chunks);
+
+        if (MODE == kModeLinear) {
+            // ---- register path, loads for the group's NEXT chunk are in flight while the current one is
+            //      transformed and stored (two chunks per group, four per SM, outstanding)
+            auto load = [&](const ChunkIter& q, uint4* v) {
+                const int m_tile = q.tile / p.num_n_tiles;
+                const int ch0 = q.c * ME::kChunk + sub * EPV;
+                const bool ch_ok = ch0 < p.Cin;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int m = m_tile * kTileM + rbase + 16 * i;
+                    v[i] = make_uint4(0u, 0u, 0u, 0u);
+                    if (ch_ok && m < p.M) v[i] = LdgNc(in + (size_t)m * p.in_pitch + p.in_coff + ch0);
+                }
+            };
+            auto process = [&](const ChunkIter& q, uint4* v) {
+                const int stage = q.it % NS;
+                const uint32_t phase = (q.it / NS) & 1u;
+                const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
+                if (has_pre) {
+                    const int ch0 = q.c * ME::kChunk + sub * EPV;
+                    float sc[EPV], sh[EPV];
+#pragma unroll
+                    for (int e = 0; e < EPV; e += 4) {
+                        float4 a = *reinterpret_cast<const float4*>(s_pre_scale + ch0 + e);
+                        float4 b = *reinterpret_cast<const float4*>(s_pre_shift + ch0 + e);
+                        sc[e] = a.x; sc[e + 1] = a.y; sc[e + 2] = a.z; sc[e + 3] = a.w;
+                        sh[e] = b.x; sh[e + 1] = b.y; sh[e + 2] = b.z; sh[e + 3] = b.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float f[EPV];
+                        ME::Unpack(v[i], f);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) {
+                            float t = fmaf(f[e], sc[e], sh[e]);
+                            f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
+                        }
+                        v[i] = ME::Pack(f);  // rows past M / channels past Cin feed accumulator rows/steps nobody reads
+                    }
+                }
+                MbarWait(&empty_bar[stage], phase ^ 1u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) StsV4(a_base + sw_off[i], v[i]);
+                FenceProxyAsync();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                MbarArrive(&full_bar[stage]);
+            };
+            uint4 v0[8], v1[8];
+            if (cur.tile < num_tiles) {
+                load(cur, v0);
+                for (;;) {
+                    ChunkIter n1 = cur;
+                    n1.Step(2, p.num_chunks);
+                    const bool h1 = n1.tile < num_tiles;
+                    if (h1) load(n1, v1);
+                    process(cur, v0);
+                    if (!h1) break;
+                    ChunkIter n2 = n1;
+                    n2.Step(2, p.num_chunks);
+                    const bool h2 = n2.tile < num_tiles;
+                    if (h2) load(n2, v0);
+                    process(n1, v1);
+                    if (!h2) break;
+                    cur = n2;
                 }
             }
-            for (int c = 0; c < p.num_chunks; ++c, ++it) {
-                if ((int)(it & 1u) != group) continue;
-                const int stage = it % NS;
-                const uint32_t phase = (it / NS) & 1u;
+        } else if (MODE == kModeGather || MODE == kModeStem) {
+            // ---- cp.async path: up to kDepth chunks per group in flight, no registers held
+            constexpr int kDepth = (NS - 2) / 2;  // 2*kDepth < NS, or the ring would deadlock on its own lag
+            RowInfo ri;
+            int decoded_tile = -1;
+            uint32_t k = 0;  // chunks issued by this group
+            for (; cur.tile < num_tiles; cur.Step(2, p.num_chunks), ++k) {
+                if (cur.tile != decoded_tile) {
+                    DecodeRows<MODE>(p, cur.tile / p.num_n_tiles, rbase, ri);
+                    decoded_tile = cur.tile;
+                }
+                const int stage = cur.it % NS;
+                const uint32_t phase = (cur.it / NS) & 1u;
                 const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
-                uint4 v[8];
+                MbarWait(&empty_bar[stage], phase ^ 1u);
                 if (MODE == kModeStem) {
-                    // chunk c = filter rows 2c, 2c+1; a row is 8 pixels x 4 channels (64 B); this thread owns
+                    // chunk c = filter rows 2c, 2c+1; a filter row is 8 pixels x 4 channels (64 B); this thread owns
                     // 2 pixels of one filter row: piece = sub & 3, filter row = 2c + (sub >> 2)
-                    const int r = 2 * c + (sub >> 2);
+                    const int r = 2 * cur.c + (sub >> 2);
                     const int dx = 2 * (sub & 3);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u);
-                        if (pix[i] >= 0 && r < p.R) {
-                            int iy = (oyx[i] >> 16) + r;
-                            int ix = (int)(short)(oyx[i] & 0xFFFF) + dx;
-                            if (iy >= 0 && iy < p.H) {
-                                const MmaT* row = in + ((size_t)pix[i] + (size_t)iy * p.W) * p.in_pitch;
-                                if (ix >= 0 && ix < p.W) a = LdgNc8(row + (size_t)ix * p.in_pitch);
-                                if (ix + 1 >= 0 && ix + 1 < p.W) b = LdgNc8(row + (size_t)(ix + 1) * p.in_pitch);
-                            }
-                        }
-                        v[i] = make_uint4(a.x, a.y, b.x, b.y);
-                    }
-                    MbarWait(&empty_bar[stage], phase ^ 1u);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        int row = rbase + 16 * i;
-                        StsV4(a_base + row * kRowBytes + ((sub ^ (row & 7)) << 4), v[i]);
+                        int iy = (ri.oyx[i] >> 16) + r;
+                        int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + dx;
+                        bool rok = ri.pix[i] >= 0 && r < p.R && iy >= 0 && iy < p.H;
+                        bool ok0 = rok && ix >= 0 && ix < p.W, ok1 = rok && ix + 1 >= 0 && ix + 1 < p.W;
+                        const MmaT* row = in + ((size_t)(rok ? ri.pix[i] : 0) + (size_t)(rok ? iy : 0) * p.W) * p.in_pitch;
+                        CpAsync8(a_base + sw_off[i], ok0 ? row + (size_t)ix * p.in_pitch : in, ok0);
+                        CpAsync8(a_base + sw_off[i] + 8, ok1 ? row + (size_t)(ix + 1) * p.in_pitch : in, ok1);
                     }
                 } else {
-                    const int tap = c / p.chunks_per_tap, j = c - tap * p.chunks_per_tap;
+                    const int tap = cur.c / p.chunks_per_tap, j = cur.c - tap * p.chunks_per_tap;
                     const int fr = tap / p.S, fs = tap - fr * p.S;
                     const int ch0 = j * ME::kChunk + sub * EPV;
                     const bool ch_ok = ch0 < p.Cin;
-                    float sc[EPV], sh[EPV];
-                    const bool has_pre = p.pre_scale != nullptr;
-                    if (has_pre && ch_ok) {
 #pragma unroll
-                        for (int e = 0; e < EPV; e += 4) {
-                            float4 a = *reinterpret_cast<const float4*>(p.pre_scale + ch0 + e);
-                            float4 b = *reinterpret_cast<const float4*>(p.pre_shift + ch0 + e);
-                            sc[e] = a.x; sc[e + 1] = a.y; sc[e + 2] = a.z; sc[e + 3] = a.w;
-                            sh[e] = b.x; sh[e + 1] = b.y; sh[e + 2] = b.z; sh[e + 3] = b.w;
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        int iy = (ri.oyx[i] >> 16) + fr;
+                        int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + fs;
+                        bool ok = ch_ok && ri.pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                        const MmaT* src = ok ? in + ((size_t)ri.pix[i] + (size_t)iy * p.W + ix) * p.in_pitch + p.in_coff + ch0 : in;
+                        CpAsync16(a_base + sw_off[i], src, ok);  // src-size 0 => 16 bytes of zeros (padding)
                     }
-                    if (MODE == kModeGeneric) {
-                        bool ok[8];
+                }
+                CpAsyncCommit();
+                if (k >= kDepth) {
+                    CpAsyncWait<kDepth>();  // the chunk issued kDepth iterations ago has landed
+                    FenceProxyAsync();
+                    MbarArrive(&full_bar[(cur.it - 2 * kDepth) % NS]);
+                }
+            }
+            CpAsyncWait<0>();
+            FenceProxyAsync();
+            {
+                // drain: arrive for the last min(k, kDepth) chunks, oldest first
+                uint32_t pending = k < (uint32_t)kDepth ? k : (uint32_t)kDepth;
+                uint32_t last_it = (uint32_t)group + 2u * (k - 1u);
+                for (uint32_t d = pending; d >= 1; --d) MbarArrive(&full_bar[(last_it - 2u * (d - 1u)) % NS]);
+            }
+        } else {
+            // ---- register paths with per-row address decode (prologue + window, or 2x2 pooled prologue)
+            RowInfo ri;
+            int decoded_tile = -1;
+            for (; cur.tile < num_tiles; cur.Step(2, p.num_chunks)) {
+                if (cur.tile != decoded_tile) {
+                    DecodeRows<MODE>(p, cur.tile / p.num_n_tiles, rbase, ri);
+                    decoded_tile = cur.tile;
+                }
+                const int stage = cur.it % NS;
+                const uint32_t phase = (cur.it / NS) & 1u;
+                const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
+                const int tap = cur.c / p.chunks_per_tap, j = cur.c - tap * p.chunks_per_tap;
+                const int fr = tap / p.S, fs = tap - fr * p.S;
+                const int ch0 = j * ME::kChunk + sub * EPV;
+                const bool ch_ok = ch0 < p.Cin;
+                float sc[EPV], sh[EPV];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            int iy = (oyx[i] >> 16) + fr;
-                            int ix = (int)(short)(oyx[i] & 0xFFFF) + fs;
-                            ok[i] = ch_ok && pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                            v[i] = make_uint4(0u, 0u, 0u, 0u);
-                            if (ok[i]) v[i] = LdgNc(in + ((size_t)pix[i] + (size_t)iy * p.W + ix) * p.in_pitch + p.in_coff + ch0);
+                for (int e = 0; e < EPV; ++e) {
+                    sc[e] = has_pre ? s_pre_scale[ch0 + e] : 1.f;
+                    sh[e] = has_pre ? s_pre_shift[ch0 + e] : 0.f;
+                }
+                if (MODE == kModeGatherPre) {
+                    uint4 v[8];
+                    bool ok[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        int iy = (ri.oyx[i] >> 16) + fr;
+                        int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + fs;
+                        ok[i] = ch_ok && ri.pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                        v[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (ok[i]) v[i] = LdgNc(in + ((size_t)ri.pix[i] + (size_t)iy * p.W + ix) * p.in_pitch + p.in_coff + ch0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (!ok[i]) continue;  // padding stays exactly zero
+                        float f[EPV];
+                        ME::Unpack(v[i], f);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) {
+                            float t = fmaf(f[e], sc[e], sh[e]);
+                            f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
                         }
-                        if (has_pre) {
+                        v[i] = ME::Pack(f);
+                    }
+                    MbarWait(&empty_bar[stage], phase ^ 1u);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                if (!ok[i]) continue;  // padding stays exactly zero
-                                float f[EPV];
-                                ME::Unpack(v[i], f);
+                    for (int i = 0; i < 8; ++i) StsV4(a_base + sw_off[i], v[i]);
+                } else {  // kModePool2: A row = mean of the 2x2 input pixels after the prologue
+                    MbarWait(&empty_bar[stage], phase ^ 1u);
 #pragma unroll
-                                for (int e = 0; e < EPV; ++e) {
-                                    float t = fmaf(f[e], sc[e], sh[e]);
-                                    f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
-                                }
-                                v[i] = ME::Pack(f);
+                    for (int half = 0; half < 2; ++half) {
+                        uint4 q[4][4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            int ii = half * 4 + i;
+                            bool ok = ch_ok && ri.pix[ii] >= 0;
+                            int iy = (ri.oyx[ii] >> 16), ix = (int)(short)(ri.oyx[ii] & 0xFFFF);
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) {
+                                q[i][d] = make_uint4(0u, 0u, 0u, 0u);
+                                if (ok) q[i][d] = LdgNc(in + ((size_t)ri.pix[ii] + (size_t)(iy + (d >> 1)) * p.W + ix + (d & 1)) * p.in_pitch + p.in_coff + ch0);
                             }
                         }
-                        MbarWait(&empty_bar[stage], phase ^ 1u);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            int row = rbase + 16 * i;
-                            StsV4(a_base + row * kRowBytes + ((sub ^ (row & 7)) << 4), v[i]);
-                        }
-                    } else {  // kModePool2: A row = mean of the 2x2 input pixels after the prologue
-                        MbarWait(&empty_bar[stage], phase ^ 1u);
+                        for (int i = 0; i < 4; ++i) {
+                            int ii = half * 4 + i;
+                            float acc[EPV];
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            uint4 q[4][4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                int ii = half * 4 + i;
-                                bool ok = ch_ok && pix[ii] >= 0;
-                                int iy = (oyx[ii] >> 16), ix = (int)(short)(oyx[ii] & 0xFFFF);
+                            for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
+                            if (ch_ok && ri.pix[ii] >= 0) {
 #pragma unroll
                                 for (int d = 0; d < 4; ++d) {
-                                    q[i][d] = make_uint4(0u, 0u, 0u, 0u);
-                                    if (ok) q[i][d] = LdgNc(in + ((size_t)pix[ii] + (size_t)(iy + (d >> 1)) * p.W + ix + (d & 1)) * p.in_pitch + p.in_coff + ch0);
-                                }
-                            }
+                                    float f[EPV];
+                                    ME::Unpack(q[i][d], f);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                int ii = half * 4 + i;
-                                float acc[EPV];
-#pragma unroll
-                                for (int e = 0; e < EPV; ++e) acc[e] = 0.f;
-                                if (ch_ok && pix[ii] >= 0) {
-#pragma unroll
-                                    for (int d = 0; d < 4; ++d) {
-                                        float f[EPV];
-                                        ME::Unpack(q[i][d], f);
-#pragma unroll
-                                        for (int e = 0; e < EPV; ++e) {
-                                            float t = has_pre ? fmaf(f[e], sc[e], sh[e]) : f[e];
-                                            acc[e] += p.pre_relu ? fmaxf(t, 0.f) : t;
-                                        }
+                                    for (int e = 0; e < EPV; ++e) {
+                                        float t = fmaf(f[e], sc[e], sh[e]);
+                                        acc[e] += p.pre_relu ? fmaxf(t, 0.f) : t;
                                     }
-#pragma unroll
-                                    for (int e = 0; e < EPV; ++e) acc[e] *= 0.25f;
                                 }
-                                int row = rbase + 16 * ii;
-                                StsV4(a_base + row * kRowBytes + ((sub ^ (row & 7)) << 4), ME::Pack(acc));
+#pragma unroll
+                                for (int e = 0; e < EPV; ++e) acc[e] *= 0.25f;
                             }
+                            StsV4(a_base + sw_off[ii], ME::Pack(acc));
                         }
                     }
                 }
-                FenceProxyAsync();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                FenceProxyAsync();
                 MbarArrive(&full_bar[stage]);
             }
         }
@@ -448,31 +613,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 if (m < p.M && co0 < p.Cout) {
                     float f[32];
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        int co = co0 + q;
-                        float t = __uint_as_float(r[q]);
-                        if (co < p.Cout) {
-                            t *= p.out_scale[co];
-                            if (p.bias) t += p.bias[co];
-                        }
-                        f[q] = p.post_relu ? fmaxf(t, 0.f) : t;
+                    for (int q = 0; q < 32; q += 4) {
+                        float4 s4 = *reinterpret_cast<const float4*>(s_out_scale + co0 + q);  // smem broadcast
+                        float4 b4 = *reinterpret_cast<const float4*>(s_bias + co0 + q);
+                        f[q] = fmaf(__uint_as_float(r[q]), s4.x, b4.x);
+                        f[q + 1] = fmaf(__uint_as_float(r[q + 1]), s4.y, b4.y);
+                        f[q + 2] = fmaf(__uint_as_float(r[q + 2]), s4.z, b4.z);
+                        f[q + 3] = fmaf(__uint_as_float(r[q + 3]), s4.w, b4.w);
+                    }
+                    if (p.post_relu) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.f);
                     }
                     if (sizeof(OutT) == 2) {
 #pragma unroll
-                        for (int q = 0; q < 32; q += 8) {
-                            if (co0 + q < p.Cout) {
-                                uint4 w = MmaElem<__nv_bfloat16>::Pack(f + q);
-                                *reinterpret_cast<uint4*>(orow + co0 + q) = w;
-                            }
-                        }
+                        for (int q = 0; q < 32; q += 8)
+                            if (co0 + q < p.Cout) *reinterpret_cast<uint4*>(orow + co0 + q) = MmaElem<__nv_bfloat16>::Pack(f + q);
                     } else {
 #pragma unroll
-                        for (int q = 0; q < 32; q += 16) {
-                            if (co0 + q < p.Cout) {
-                                uint4 w = MmaElem<__nv_fp8_e4m3>::Pack(f + q);
-                                *reinterpret_cast<uint4*>(orow + co0 + q) = w;
-                            }
-                        }
+                        for (int q = 0; q < 32; q += 16)
+                            if (co0 + q < p.Cout) *reinterpret_cast<uint4*>(orow + co0 + q) = MmaElem<__nv_fp8_e4m3>::Pack(f + q);
                     }
                 }
             }
@@ -543,6 +703,244 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
 }
 
+// =====================================================================================================
+// 3x3 / stride 1 / pad 1 convolution with the input patch staged ONCE in shared memory ("halo" kernel).
+//
+// The gather kernel above re-reads every input pixel 9 times from L2 (once per filter tap); with only
+// Cout = 32 output channels per dense layer that makes the 3x3 convs L2-bandwidth bound.  Here a CTA owns a
+// TH x TW patch of output pixels of one image, loads the (TH+2) x 16 input pixels (zero filled outside the
+// image) once, and runs the 9 taps as 9 row-SHIFTED views of the same shared-memory tile:
+//   output row m' = y*16 + x   reads patch pixel  q = m' + fr*16 + fs        (fr, fs = filter tap)
+// so each tap is the same UMMA A operand with its start address advanced by (fr*16 + fs) rows.  Row shifts
+// that are not a multiple of 8 are incompatible with the swizzled layouts, so A uses the non-swizzled
+// K-major canonical layout with rows 16 bytes apart: one "plane" [pixel][16 B] per 16-byte K piece
+// (LBO = plane stride, SBO = 128 B).  Columns x >= TW of a tile are junk rows that are never stored.
+// All 9 x (Cin/chunk) weight tiles stay resident in shared memory for the lifetime of the CTA.
+constexpr int kHaloPW = 16;                       // padded patch width (TW <= 14)
+constexpr int kHaloPatchPixels = 10 * kHaloPW + 8;  // (TH+2 <= 10) rows + slack for the junk rows' overreach
+constexpr int kHaloPlaneStride = kHaloPatchPixels * 16 + 16;  // +16 B: planes start in different banks
+constexpr int kHaloMaxPieces = 16;                // Cin * esz / 16 <= 16  (128 bf16 or 256 e4m3... capped by Cin<=128)
+constexpr int kHaloPatchBytes = ((kHaloMaxPieces * kHaloPlaneStride + 1023) / 1024) * 1024;
+constexpr int kHaloWeightBytes = 18 * 32 * kRowBytes;  // 9 taps x <=2 chunks x [32][128 B]
+constexpr int kHaloSmemBytes = 1024 + kHaloWeightBytes + 2 * kHaloPatchBytes + 2 * 32 * 4 + 256;
+
+struct HParams {
+    const void* in;
+    void* out;
+    const float* out_scale;
+    const float* bias;
+    int post_relu;
+    int H, W, in_pitch, in_coff, out_pitch, out_coff, Cin, Cout;
+    int n, TH, TW, tiles_x, tiles_y, num_tiles;
+    int chunks_per_tap;  // weight chunks (128 B of K) per tap
+};
+
+__device__ __forceinline__ uint64_t MakeSmemDescNoSwizzle(uint32_t smem_byte_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;  // layout_type 0 = SWIZZLE_NONE
+}
+
+template <typename MmaT, typename OutT>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HParams p) {
+    using ME = MmaElem<MmaT>;
+    constexpr int EPV = ME::kPerVec;
+    constexpr int BN = 32;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                                  // resident weights, SW128 K-major tiles of 4 KB
+    uint8_t* s_patch = smem + kHaloWeightBytes;           // 2 patch buffers
+    float* s_out_scale = reinterpret_cast<float*>(s_patch + 2 * kHaloPatchBytes);
+    float* s_bias = s_out_scale + 32;
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_bias + 32);
+    uint64_t* patch_full = w_bar + 1;
+    uint64_t* patch_empty = patch_full + 2;
+    uint64_t* tmem_full = patch_empty + 2;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pieces = p.Cin / EPV;               // 16-byte K pieces per pixel
+    const int num_wtiles = 9 * p.chunks_per_tap;  // resident weight tiles
+
+    if (warp == 12 && lane == 0) {
+        MbarInit(w_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            MbarInit(&patch_full[b], 256);
+            MbarInit(&patch_empty[b], 1);
+            MbarInit(&tmem_full[b], 1);
+            MbarInit(&tmem_empty[b], 128);
+        }
+        FenceBarrierInit();
+        PrefetchTensorMap(&tmap_w);
+    }
+    if (warp == 13) TmemAlloc(tmem_slot, 64);
+    if (threadIdx.x < 32) {
+        s_out_scale[threadIdx.x] = threadIdx.x < p.Cout ? p.out_scale[threadIdx.x] : 0.f;
+        s_bias[threadIdx.x] = (p.bias && threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
+    }
+    // the slack pixels past the patch are read by junk rows only, but must never hold NaN-producing garbage
+    // for rows that ARE stored: they are not (junk rows only); still, clear both buffers once for hygiene
+    for (int i = threadIdx.x; i < 2 * kHaloPatchBytes / 16; i += kThreads)
+        reinterpret_cast<uint4*>(s_patch)[i] = make_uint4(0u, 0u, 0u, 0u);
+    FenceProxyAsync();
+    TcFenceBefore();
+    __syncthreads();
+    TcFenceAfter();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // =========================================================== patch producers (256 threads, cp.async)
+        const MmaT* in = reinterpret_cast<const MmaT*>(p.in);
+        const int tid = threadIdx.x;  // 0..255
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
+            const int buf = k & 1;
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+            const int iy0 = ty * p.TH - 1, ix0 = tx * p.TW - 1;
+            const int rows = p.TH + 2;
+            const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes);
+            MbarWait(&patch_empty[buf], ((k >> 1) & 1u) ^ 1u);
+            const int total = rows * kHaloPW * pieces;
+            for (int e = tid; e < total; e += 256) {
+                const int kp = e % pieces, q = e / pieces;
+                const int py = q / kHaloPW, px = q - py * kHaloPW;
+                const int iy = iy0 + py, ix = ix0 + px;
+                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const MmaT* src = ok ? in + ((size_t)(img * p.H + iy) * p.W + ix) * p.in_pitch + p.in_coff + kp * EPV : in;
+                CpAsync16(pbase + kp * kHaloPlaneStride + q * 16, src, ok);
+            }
+            CpAsyncCommit();
+            if (k >= 1) {
+                CpAsyncWait<1>();  // the previous tile's patch has landed
+                FenceProxyAsync();
+                MbarArrive(&patch_full[(k - 1) & 1]);
+            }
+        }
+        CpAsyncWait<0>();
+        FenceProxyAsync();
+        if (k >= 1) MbarArrive(&patch_full[(k - 1) & 1]);
+    } else if (warp < 12) {
+        // =========================================================== epilogue
+        const int e = warp & 3;
+        OutT* out = reinterpret_cast<OutT*>(p.out);
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
+            const uint32_t acc = k & 1u, acc_phase = (k >> 1) & 1u;
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+            MbarWait(&tmem_full[acc], acc_phase);
+            TcFenceAfter();
+            uint32_t r[32];
+            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * BN, r);
+            TmemLoadWait();
+            TcFenceBefore();
+            MbarArrive(&tmem_empty[acc]);  // the accumulator is in registers: release it before the stores
+            const int mrow = e * 32 + lane;
+            const int y = mrow / kHaloPW, x = mrow - y * kHaloPW;
+            const int oy = ty * p.TH + y, ox = tx * p.TW + x;
+            if (y < p.TH && x < p.TW && oy < p.H && ox < p.W) {
+                float f[32];
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                    float4 s4 = *reinterpret_cast<const float4*>(s_out_scale + q);
+                    float4 b4 = *reinterpret_cast<const float4*>(s_bias + q);
+                    f[q] = fmaf(__uint_as_float(r[q]), s4.x, b4.x);
+                    f[q + 1] = fmaf(__uint_as_float(r[q + 1]), s4.y, b4.y);
+                    f[q + 2] = fmaf(__uint_as_float(r[q + 2]), s4.z, b4.z);
+                    f[q + 3] = fmaf(__uint_as_float(r[q + 3]), s4.w, b4.w);
+                }
+                if (p.post_relu) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.f);
+                }
+                OutT* orow = out + ((size_t)(img * p.H + oy) * p.W + ox) * p.out_pitch + p.out_coff;
+                if (sizeof(OutT) == 2) {
+#pragma unroll
+                    for (int q = 0; q < 32; q += 8)
+                        if (q < p.Cout) *reinterpret_cast<uint4*>(orow + q) = MmaElem<__nv_bfloat16>::Pack(f + q);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; q += 16)
+                        if (q < p.Cout) *reinterpret_cast<uint4*>(orow + q) = MmaElem<__nv_fp8_e4m3>::Pack(f + q);
+                }
+            }
+        }
+    } else if (warp == 12) {
+        // =========================================================== weights: TMA once, resident
+        if (lane == 0) {
+            MbarArriveExpectTx(w_bar, (uint32_t)num_wtiles * BN * kRowBytes);
+            for (int t = 0; t < num_wtiles; ++t) TmaLoad2D(s_w + t * BN * kRowBytes, &tmap_w, w_bar, t * ME::kChunk, 0);
+        }
+        __syncwarp();
+    } else {
+        // =========================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, BN);
+            MbarWait(w_bar, 0);
+            uint32_t k = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
+                const uint32_t buf = k & 1u, ph = (k >> 1) & 1u;
+                MbarWait(&tmem_empty[buf], ph ^ 1u);
+                MbarWait(&patch_full[buf], ph);
+                TcFenceAfter();
+                const uint32_t d_addr = tmem_base + buf * BN;
+                const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes);
+                const uint32_t wbase = SmemAddr(s_w);
+                uint32_t first = 1;
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int fr = tap / 3, fs = tap - fr * 3;
+                    const uint32_t shift = (uint32_t)(fr * kHaloPW + fs) * 16u;
+                    for (int j = 0; j < p.chunks_per_tap; ++j) {
+                        int valid = p.Cin - j * ME::kChunk;
+                        if (valid > ME::kChunk) valid = ME::kChunk;
+                        const int ksteps = valid / ME::kStepK;
+                        const uint64_t b_desc = MakeSmemDesc(wbase + (uint32_t)(tap * p.chunks_per_tap + j) * BN * kRowBytes);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            // K step ks of chunk j = K pieces 2*(4j+ks), +1  (a piece is 16 bytes of K)
+                            const uint32_t piece0 = (uint32_t)(j * (kRowBytes / 16) + 2 * ks);
+                            const uint64_t a_desc = MakeSmemDescNoSwizzle(pbase + piece0 * kHaloPlaneStride + shift, kHaloPlaneStride, 128);
+                            UmmaSS<ME::kKind>(d_addr, a_desc, b_desc + (uint64_t)(2 * ks), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
+                    }
+                }
+                UmmaCommit(&patch_empty[buf]);
+                UmmaCommit(&tmem_full[buf]);
+            }
+        }
+        __syncwarp();
+    }
+    TcFenceBefore();
+    __syncthreads();
+    if (warp == 13) {
+        TcFenceAfter();
+        TmemDealloc(tmem_base, 64);
+    }
+}
+
+template <typename MmaT, typename OutT>
+cudaError_t LaunchHalo(const CUtensorMap& tm, const HParams& p, cudaStream_t stream) {
+    auto kern = conv3x3_halo_kernel<MmaT, OutT>;
+    static int sm_count[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!sm_count[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmemBytes);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count[dev] = n > 0 ? n : 148;
+    }
+    int grid = p.num_tiles < sm_count[dev] ? p.num_tiles : sm_count[dev];
+    kern<<<grid, kThreads, kHaloSmemBytes, stream>>>(tm, p);
+    CountLaunch();
+    return cudaGetLastError();
+}
+
 template <typename MmaT, typename OutT, int BN, int MODE>
 cudaError_t Launch(const CUtensorMap& tm, const UParams& p, cudaStream_t stream) {
     using Cfg = TileCfg<BN>;
@@ -575,6 +973,17 @@ cudaError_t LaunchBN(int bn, const CUtensorMap& tm, const UParams& p, cudaStream
     return cudaErrorInvalidValue;
 }
 
+template <typename MmaT, typename OutT>
+cudaError_t LaunchMode(int mode, int bn, const CUtensorMap& tm, const UParams& p, cudaStream_t stream) {
+    switch (mode) {
+        case kModeLinear: return LaunchBN<MmaT, OutT, kModeLinear>(bn, tm, p, stream);
+        case kModeGather: return LaunchBN<MmaT, OutT, kModeGather>(bn, tm, p, stream);
+        case kModeGatherPre: return LaunchBN<MmaT, OutT, kModeGatherPre>(bn, tm, p, stream);
+        case kModePool2: return LaunchBN<MmaT, OutT, kModePool2>(bn, tm, p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace
 
 int UmmaKChunkElems(DType d) { return d == DType::FP8 ? 128 : 64; }
@@ -598,6 +1007,8 @@ bool UmmaSupported(const ConvArgs& a) {
     if (a.Cin % step != 0) return false;
     if ((a.in.pitch * esz_in) % 16 != 0 || (a.in.c_off * esz_in) % 16 != 0) return false;
     if (a.pool2 && !(a.R == 1 && a.S == 1 && a.in.H % 2 == 0 && a.in.W % 2 == 0)) return false;
+    if (a.Cin > kMaxCin || (a.Cout + 127) / 128 * 128 > kMaxCoutPad) return false;
+    if (it != ot) return false;  // mixed bf16 -> e4m3 only exists for the stem
     return true;
 }
 
@@ -620,19 +1031,38 @@ cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t strea
     p.num_n_tiles = w.Cout_pad / bn;
     p.chunks_per_tap = stem ? 1 : (a.Cin + kc - 1) / kc;
     p.num_chunks = stem ? w.K_pad / kc : a.R * a.S * p.chunks_per_tap;
+    p.cin_pad = stem ? 0 : p.chunks_per_tap * kc;
+    p.cout_pad = w.Cout_pad;
     const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(w.tensor_map);
     if (stem) {
         if (ot == DType::BF16) return LaunchBN<__nv_bfloat16, __nv_bfloat16, kModeStem>(bn, tm, p, stream);
         return LaunchBN<__nv_bfloat16, __nv_fp8_e4m3, kModeStem>(bn, tm, p, stream);
     }
-    if (it == DType::BF16) {
-        if (ot == DType::BF16)
-            return a.pool2 ? LaunchBN<__nv_bfloat16, __nv_bfloat16, kModePool2>(bn, tm, p, stream)
-                           : LaunchBN<__nv_bfloat16, __nv_bfloat16, kModeGeneric>(bn, tm, p, stream);
-        return cudaErrorInvalidValue;
+    // 3x3/s1/p1 with a narrow output: stage the input patch once in shared memory (9 shifted views)
+    static const bool halo_enabled = [] { const char* e = getenv("B200_ENGINE_HALO"); return !(e && e[0] == '0'); }();
+    const int step_k = it == DType::BF16 ? 16 : 32;
+    if (halo_enabled && a.R == 3 && a.S == 3 && a.stride == 1 && a.pad == 1 && !a.pre_scale && !a.pool2 && a.Cout <= 32 &&
+        a.Cin <= 128 && a.Cin % step_k == 0 && it == ot && a.in.W >= 7) {
+        HParams h;
+        h.in = a.in.base; h.out = a.out.base; h.out_scale = w.out_scale; h.bias = a.bias; h.post_relu = a.post_relu;
+        h.H = a.in.H; h.W = a.in.W; h.in_pitch = a.in.pitch; h.in_coff = a.in.c_off;
+        h.out_pitch = a.out.pitch; h.out_coff = a.out.c_off; h.Cin = a.Cin; h.Cout = a.Cout; h.n = a.n;
+        h.TW = h.W % 14 == 0 ? 14 : (h.W < 14 ? h.W : (h.W % 13 == 0 ? 13 : (h.W % 12 == 0 ? 12 : 14)));
+        h.TH = h.H % 8 == 0 ? 8 : (h.H % 7 == 0 ? 7 : (h.H < 8 ? h.H : 8));
+        h.tiles_x = (h.W + h.TW - 1) / h.TW;
+        h.tiles_y = (h.H + h.TH - 1) / h.TH;
+        h.num_tiles = a.n * h.tiles_x * h.tiles_y;
+        h.chunks_per_tap = p.chunks_per_tap;
+        if (it == DType::BF16) return LaunchHalo<__nv_bfloat16, __nv_bfloat16>(tm, h, stream);
+        return LaunchHalo<__nv_fp8_e4m3, __nv_fp8_e4m3>(tm, h, stream);
     }
-    return a.pool2 ? LaunchBN<__nv_fp8_e4m3, __nv_fp8_e4m3, kModePool2>(bn, tm, p, stream)
-                   : LaunchBN<__nv_fp8_e4m3, __nv_fp8_e4m3, kModeGeneric>(bn, tm, p, stream);
+    int mode;
+    if (a.pool2) mode = kModePool2;
+    else if (a.R == 1 && a.S == 1 && a.stride == 1 && a.pad == 0) mode = kModeLinear;
+    else mode = a.pre_scale ? kModeGatherPre : kModeGather;
+    if (it == DType::BF16 && ot == DType::BF16) return LaunchMode<__nv_bfloat16, __nv_bfloat16>(mode, bn, tm, p, stream);
+    if (it == DType::FP8 && ot == DType::FP8) return LaunchMode<__nv_fp8_e4m3, __nv_fp8_e4m3>(mode, bn, tm, p, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace kernels

@@ -430,7 +430,8 @@ private:
             TensorDesc t;
             t.name = vi.name;
             t.rank = 4; t.C = s.C; t.H = s.H; t.W = s.W;
-            t.dtype = lowp ? DType::BF16 : DType::F32;
+            // image-like inputs (C < 16) feed the bf16 stem kernel; wide inputs are stored in the activation type
+            t.dtype = !lowp ? DType::F32 : (s.C < 16 ? DType::BF16 : act_dtype_);
             t.pitch = lowp ? (s.C + 3) / 4 * 4 : s.C;
             t.buffer = NewBuffer((size_t)s.H * s.W * t.pitch, t.dtype);
             int idx = AddTensor(t);

@@ -68,8 +68,8 @@ def _conv_node(x, w, out, k, s=1, p=0, bias=None):
                           {"kernel_shape": [k, k], "strides": [s, s], "pads": [p, p, p, p], "dilations": [1, 1], "group": 1})
 
 
-CASES = ["conv1x1_bn_relu", "conv1x1_partial_chunk", "conv3x3", "stem_maxpool", "transition", "dense_block", "cout256",
-         "gap_gemm_softmax"]
+CASES = ["conv1x1_bn_relu", "conv1x1_partial_chunk", "conv3x3", "stem_maxpool", "transition", "dense_block",
+         "dense_block_copy", "cout256", "gap_gemm_softmax"]
 TOL = {"fp32": 2e-5, "bf16": 2.5e-2, "fp8": 1.5e-1}
 
 
@@ -99,8 +99,15 @@ def _build_case(case, tmp_path, rng):
         nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1),
                  onnx_lite.Node("AveragePool", ["c"], ["y"], {"kernel_shape": [2, 2], "strides": [2, 2], "pads": [0, 0, 0, 0]})]
         shp, out = (128, 12, 12), (64, 6, 6)
-    elif case == "dense_block":
-        inits, nodes, feats = {}, [], ["x"]
+    elif case in ("dense_block", "dense_block_copy"):
+        # "dense_block": the first member is produced by a kernel -> in-place concat (channel slices);
+        # "dense_block_copy": the first member is the graph input itself -> copy_channels fallback
+        inits, nodes = {}, []
+        if case == "dense_block":
+            nodes.append(onnx_lite.Node("Relu", ["x"], ["x0"]))
+            feats = ["x0"]
+        else:
+            feats = ["x"]
         c = 64
         for li in range(3):
             cat = f"cat{li}"
@@ -245,10 +252,18 @@ def test_validation_errors_match_reference_messages(pkg, repo_dir, monkeypatch):
         # output buffer smaller than the result: min(data_size, produced) bytes are written, no overflow
         y = m.infer([pkg.TensorData("input", np.ones((1, 3), np.float32))], [pkg.OutputConfig("output", [1, 1])])[0].data
         np.testing.assert_allclose(y, [[-1.6748662]], rtol=2e-6)
-        # unload while a wrapper is still held: the wrapper must stay safe to use and destroy
+        # unload while another wrapper is still held: that wrapper must stay safe to use and destroy
+        import ctypes as C
+        lib = pkg.load_library()
+        err = C.c_void_p()
+        extra = pkg.Model(lib.GetModelHandle(mgr._h, b"test_model", None, C.byref(err)), False)
+        assert extra.is_loaded()
         mgr.unload_model("test_model")
-        assert not m.is_loaded()
+        assert not extra.is_loaded()
         with pytest.raises(pkg.EngineError, match="Model not loaded"):
+            extra.infer([pkg.TensorData("input", ok)], [pkg.OutputConfig("output", [1, 2])])
+        extra.destroy()
+        with pytest.raises(pkg.EngineError, match="model handle is nil"):   # Go: "model handle is nil"
             m.infer([pkg.TensorData("input", ok)], [pkg.OutputConfig("output", [1, 2])])
     finally:
         mgr.shutdown()
