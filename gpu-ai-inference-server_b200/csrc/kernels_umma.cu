@@ -62,14 +62,27 @@ __device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // A lost arrive must become an error, not a hung GPU: trap after a generous spin budget.
+__device__ __noinline__ void MbarTimeout() {
+    printf("conv_umma: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+    __trap();
+}
 __device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
+    if (MbarTryWait(bar, parity)) return;
     uint32_t spins = 0;
     while (!MbarTryWait(bar, parity)) {
-        if (++spins > (1u << 24)) {
-            printf("conv_umma: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
+        if (++spins > (1u << 24)) MbarTimeout();
     }
+}
+// One lane of a fully converged warp; the compiler keeps the surrounding code on the uniform datapath
+// (descriptors in uniform registers) instead of wrapping every tcgen05/TMA instruction in a waterfall loop.
+__device__ __forceinline__ bool ElectOne() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void FenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -640,59 +653,60 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             MbarArrive(&tmem_empty[acc]);
         }
     } else if (warp == 12) {
-        // =========================================================== B producer (TMA)
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int n_tile = tile % p.num_n_tiles;
-                for (int c = 0; c < p.num_chunks; ++c, ++it) {
-                    const int stage = it % NS;
-                    const uint32_t phase = (it / NS) & 1u;
-                    MbarWait(&empty_bar[stage], phase ^ 1u);
+        // =========================================================== B producer (TMA); whole warp converged, one lane issues
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.num_n_tiles;
+            for (int c = 0; c < p.num_chunks; ++c, ++it) {
+                const int stage = it % NS;
+                const uint32_t phase = (it / NS) & 1u;
+                MbarWait(&empty_bar[stage], phase ^ 1u);
+                if (ElectOne()) {
                     MbarArriveExpectTx(&full_bar[stage], BN * kRowBytes);
                     TmaLoad2D(smem + stage * Cfg::kStageBytes + kATileBytes, &tmap_w, &full_bar[stage], c * ME::kChunk, n_tile * BN);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, BN);
-            uint32_t it = 0, tile_iter = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
-                const uint32_t acc = tile_iter & 1u, acc_phase = (tile_iter >> 1) & 1u;
-                MbarWait(&tmem_empty[acc], acc_phase ^ 1u);
+        // =========================================================== MMA issuer; whole warp converged, one lane issues
+        constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, BN);
+        const uint64_t stage_desc = MakeSmemDesc(SmemAddr(smem));
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        uint32_t it = 0, tile_iter = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
+            const uint32_t acc = tile_iter & 1u, acc_phase = (tile_iter >> 1) & 1u;
+            MbarWait(&tmem_empty[acc], acc_phase ^ 1u);
+            TcFenceAfter();
+            const uint32_t d_addr = tmem_u + acc * BN;
+            int j = 0;  // chunk index inside the current filter tap
+            for (int c = 0; c < p.num_chunks; ++c, ++it) {
+                const int stage = it % NS;
+                const uint32_t phase = (it / NS) & 1u;
+                int ksteps;  // K steps of this chunk that carry data
+                if (MODE == kModeStem) {
+                    ksteps = (p.R - 2 * c >= 2 ? 2 : 1) * (32 / ME::kStepK);
+                } else {
+                    int valid = p.Cin - j * ME::kChunk;
+                    ksteps = valid >= ME::kChunk ? ME::kChunk / ME::kStepK : valid / ME::kStepK;
+                    if (++j == p.chunks_per_tap) j = 0;
+                }
+                const uint64_t a_desc = stage_desc + (uint64_t)((uint32_t)stage * (Cfg::kStageBytes >> 4));
+                const uint64_t b_desc = a_desc + (uint64_t)(kATileBytes >> 4);
+                MbarWait(&full_bar[stage], phase);
                 TcFenceAfter();
-                const uint32_t d_addr = tmem_base + acc * BN;
-                for (int c = 0; c < p.num_chunks; ++c, ++it) {
-                    const int stage = it % NS;
-                    const uint32_t phase = (it / NS) & 1u;
-                    int valid;  // elements of this chunk that carry data
-                    if (MODE == kModeStem) {
-                        valid = (p.R - 2 * c >= 2 ? 2 : 1) * 32;
-                    } else {
-                        int j = c % p.chunks_per_tap;
-                        valid = p.Cin - j * ME::kChunk;
-                        if (valid > ME::kChunk) valid = ME::kChunk;
-                    }
-                    const int ksteps = (valid + ME::kStepK - 1) / ME::kStepK;
-                    MbarWait(&full_bar[stage], phase);
-                    TcFenceAfter();
-                    const uint32_t a_addr = SmemAddr(smem + stage * Cfg::kStageBytes);
-                    const uint64_t a_desc = MakeSmemDesc(a_addr);
-                    const uint64_t b_desc = MakeSmemDesc(a_addr + kATileBytes);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        // +32 bytes per K step inside the 128-byte swizzle row (start-address field is >>4)
-                        UmmaSS<ME::kKind>(d_addr, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc,
-                                          (c > 0 || ks > 0) ? 1u : 0u);
-                    }
+                if (ElectOne()) {
+                    // +32 bytes per K step inside the 128-byte swizzle row (start-address field is >>4)
+                    UmmaSS<ME::kKind>(d_addr, a_desc, b_desc, idesc, c > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 1; ks < ME::kChunk / ME::kStepK; ++ks)
+                        if (ks < ksteps) UmmaSS<ME::kKind>(d_addr, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, 1u);
                     UmmaCommit(&empty_bar[stage]);
                     if (c == p.num_chunks - 1) UmmaCommit(&tmem_full[acc]);
                 }
+                __syncwarp();
             }
         }
-        __syncwarp();
     }
 
     TcFenceBefore();
@@ -805,8 +819,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
             const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes);
             MbarWait(&patch_empty[buf], ((k >> 1) & 1u) ^ 1u);
             const int total = rows * kHaloPW * pieces;
+            constexpr int kFullPieces = 128 / EPV;
             for (int e = tid; e < total; e += 256) {
-                const int kp = e % pieces, q = e / pieces;
+                const int kp = pieces == kFullPieces ? e % kFullPieces : e % pieces;
+                const int q = pieces == kFullPieces ? e / kFullPieces : e / pieces;
                 const int py = q / kHaloPW, px = q - py * kHaloPW;
                 const int iy = iy0 + py, ix = ix0 + px;
                 const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
@@ -870,48 +886,65 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         }
     } else if (warp == 12) {
         // =========================================================== weights: TMA once, resident
-        if (lane == 0) {
+        if (ElectOne()) {
             MbarArriveExpectTx(w_bar, (uint32_t)num_wtiles * BN * kRowBytes);
             for (int t = 0; t < num_wtiles; ++t) TmaLoad2D(s_w + t * BN * kRowBytes, &tmap_w, w_bar, t * ME::kChunk, 0);
         }
         __syncwarp();
     } else {
-        // =========================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, BN);
-            MbarWait(w_bar, 0);
-            uint32_t k = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
-                const uint32_t buf = k & 1u, ph = (k >> 1) & 1u;
-                MbarWait(&tmem_empty[buf], ph ^ 1u);
-                MbarWait(&patch_full[buf], ph);
-                TcFenceAfter();
-                const uint32_t d_addr = tmem_base + buf * BN;
-                const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes);
-                const uint32_t wbase = SmemAddr(s_w);
-                uint32_t first = 1;
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int fr = tap / 3, fs = tap - fr * 3;
-                    const uint32_t shift = (uint32_t)(fr * kHaloPW + fs) * 16u;
-                    for (int j = 0; j < p.chunks_per_tap; ++j) {
-                        int valid = p.Cin - j * ME::kChunk;
-                        if (valid > ME::kChunk) valid = ME::kChunk;
-                        const int ksteps = valid / ME::kStepK;
-                        const uint64_t b_desc = MakeSmemDesc(wbase + (uint32_t)(tap * p.chunks_per_tap + j) * BN * kRowBytes);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            // K step ks of chunk j = K pieces 2*(4j+ks), +1  (a piece is 16 bytes of K)
-                            const uint32_t piece0 = (uint32_t)(j * (kRowBytes / 16) + 2 * ks);
-                            const uint64_t a_desc = MakeSmemDescNoSwizzle(pbase + piece0 * kHaloPlaneStride + shift, kHaloPlaneStride, 128);
-                            UmmaSS<ME::kKind>(d_addr, a_desc, b_desc + (uint64_t)(2 * ks), idesc, first ? 0u : 1u);
-                            first = 0;
+        // =========================================================== MMA issuer; whole warp converged, one lane issues
+        constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, BN);
+        const uint64_t a_base = MakeSmemDescNoSwizzle(SmemAddr(s_patch), kHaloPlaneStride, 128);
+        const uint64_t b_base = MakeSmemDesc(SmemAddr(s_w));
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        MbarWait(w_bar, 0);
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
+            const uint32_t buf = k & 1u, ph = (k >> 1) & 1u;
+            MbarWait(&tmem_empty[buf], ph ^ 1u);
+            MbarWait(&patch_full[buf], ph);
+            TcFenceAfter();
+            const uint32_t d_addr = tmem_u + buf * BN;
+            const uint64_t a0 = a_base + (uint64_t)(buf * (kHaloPatchBytes >> 4));
+            constexpr int CPT = 128 / ME::kChunk;  // chunks per tap when Cin == 128
+            if (ElectOne()) {
+                if (p.Cin == 128) {
+                    // fully unrolled: every descriptor is base + compile-time constant
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint32_t aoff = (uint32_t)(((j * 8 + 2 * ks) * kHaloPlaneStride) / 16 + (tap / 3) * kHaloPW + (tap % 3));
+                                const uint32_t boff = (uint32_t)(((tap * CPT + j) * BN * kRowBytes) / 16 + 2 * ks);
+                                UmmaSS<ME::kKind>(d_addr, a0 + (uint64_t)aoff, b_base + (uint64_t)boff, idesc, (tap | j | ks) ? 1u : 0u);
+                            }
+                        }
+                    }
+                } else {
+                    uint32_t first = 1;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t shift = (uint32_t)((tap / 3) * kHaloPW + (tap % 3));
+                        for (int j = 0; j < p.chunks_per_tap; ++j) {
+                            int valid = p.Cin - j * ME::kChunk;
+                            if (valid > ME::kChunk) valid = ME::kChunk;
+                            const int ksteps = valid / ME::kStepK;
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                // a K piece is 16 bytes of K (one plane); 8 pieces per 128-byte weight chunk
+                                const uint32_t aoff = (uint32_t)((j * 8 + 2 * ks) * (kHaloPlaneStride / 16)) + shift;
+                                const uint32_t boff = (uint32_t)((tap * p.chunks_per_tap + j) * (BN * kRowBytes / 16) + 2 * ks);
+                                UmmaSS<ME::kKind>(d_addr, a0 + (uint64_t)aoff, b_base + (uint64_t)boff, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
                         }
                     }
                 }
                 UmmaCommit(&patch_empty[buf]);
                 UmmaCommit(&tmem_full[buf]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
     TcFenceBefore();
     __syncthreads();
