@@ -249,16 +249,16 @@ struct UParams {
 
 // A-producer flavours
 enum : int {
-    kModeLinear = 0,     // 1x1, stride 1, no padding: input pixel == output pixel; register path, optional prologue
-    kModeGather = 1,     // RxS window with zero padding, no prologue: cp.async (LDGSTS) with zero fill, deep pipeline
-    kModeGatherPre = 2,  // RxS window WITH prologue (not used by DenseNet): register path
+    kModeLinear = 0,     // 1x1, stride 1, no padding: input pixel == output pixel; cp.async, optional in-place prologue
+    kModeGather = 1,     // RxS window with zero padding: cp.async (LDGSTS) with zero fill, optional in-place prologue
     kModePool2 = 3,      // 1x1 on the 2x2 average of the prologue-transformed input (transition layers)
     kModeStem = 4        // 7x7/s2 on a 3(+1 pad)-channel image: 8-byte cp.async, 8 pixels x 4 channels per filter row
 };
 
-constexpr int kMaxCin = 2048;       // prologue vectors staged in shared memory
+constexpr int kMaxCin = 1536;       // prologue vectors staged in shared memory
 constexpr int kMaxCoutPad = 1024;   // epilogue vectors staged in shared memory
-constexpr int kVecSmemBytes = (2 * kMaxCin + 2 * kMaxCoutPad) * 4;
+constexpr int kEpiStageBytes = 4 * 32 * 80;
+constexpr int kVecSmemBytes = (2 * kMaxCin + 2 * kMaxCoutPad) * 4 + kEpiStageBytes;
 
 template <int BN> struct TileCfg {
     static constexpr int kStageBytes = kATileBytes + BN * kRowBytes;
@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     float* s_pre_shift = s_pre_scale + kMaxCin;
     float* s_out_scale = s_pre_shift + kMaxCin;
     float* s_bias = s_out_scale + kMaxCoutPad;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + kMaxCoutPad);
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + kMaxCoutPad);  // 4 epilogue warps x 32 rows x 80 B
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stage + kEpiStageBytes);
     uint64_t* empty_bar = full_bar + NS;
     uint64_t* tmem_full = empty_bar + NS;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -389,85 +390,74 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         ChunkIter cur;
         cur.Init(group, p.num_chunks);
 
-        if (MODE == kModeLinear) {
-            // ---- register path, loads for the group's NEXT chunk are in flight while the current one is
-            //      transformed and stored (two chunks per group, four per SM, outstanding)
-            auto load = [&](const ChunkIter& q, uint4* v) {
-                const int m_tile = q.tile / p.num_n_tiles;
-                const int ch0 = q.c * ME::kChunk + sub * EPV;
-                const bool ch_ok = ch0 < p.Cin;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    int m = m_tile * kTileM + rbase + 16 * i;
-                    v[i] = make_uint4(0u, 0u, 0u, 0u);
-                    if (ch_ok && m < p.M) v[i] = LdgNc(in + (size_t)m * p.in_pitch + p.in_coff + ch0);
-                }
-            };
-            auto process = [&](const ChunkIter& q, uint4* v) {
+        if (MODE == kModeLinear || MODE == kModeGather || MODE == kModeStem) {
+            // ---- cp.async path: up to kDepth chunks per group in flight with no registers held.  When the layer
+            //      has a prologue (folded BN + ReLU) each thread transforms, IN PLACE, exactly the 16-byte pieces
+            //      it copied itself once they have landed (so no cross-thread hazard, no extra staging buffer).
+            constexpr int kDepth = (NS - 2) / 2;  // 2*kDepth < NS, or the ring would deadlock on its own lag
+            RowInfo ri, ri_tail;
+            int decoded_tile = -1, decoded_tail = -1;
+            ChunkIter tail = cur;
+            uint32_t k = 0;  // chunks issued by this group
+
+            auto finish = [&](const ChunkIter& q) {  // chunk q has landed: optional in-place prologue, then publish
                 const int stage = q.it % NS;
-                const uint32_t phase = (q.it / NS) & 1u;
-                const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
-                if (has_pre) {
-                    const int ch0 = q.c * ME::kChunk + sub * EPV;
-                    float sc[EPV], sh[EPV];
-#pragma unroll
-                    for (int e = 0; e < EPV; e += 4) {
-                        float4 a = *reinterpret_cast<const float4*>(s_pre_scale + ch0 + e);
-                        float4 b = *reinterpret_cast<const float4*>(s_pre_shift + ch0 + e);
-                        sc[e] = a.x; sc[e + 1] = a.y; sc[e + 2] = a.z; sc[e + 3] = a.w;
-                        sh[e] = b.x; sh[e + 1] = b.y; sh[e + 2] = b.z; sh[e + 3] = b.w;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float f[EPV];
-                        ME::Unpack(v[i], f);
-#pragma unroll
-                        for (int e = 0; e < EPV; ++e) {
-                            float t = fmaf(f[e], sc[e], sh[e]);
-                            f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
+                if (MODE != kModeStem && has_pre) {
+                    const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
+                    int ch0, fr = 0, fs = 0;
+                    if (MODE == kModeLinear) {
+                        ch0 = q.c * ME::kChunk + sub * EPV;
+                    } else {
+                        const int tap = q.c / p.chunks_per_tap, j = q.c - tap * p.chunks_per_tap;
+                        fr = tap / p.S;
+                        fs = tap - fr * p.S;
+                        ch0 = j * ME::kChunk + sub * EPV;
+                        if (q.tile != decoded_tail) {
+                            DecodeRows<MODE>(p, q.tile / p.num_n_tiles, rbase, ri_tail);
+                            decoded_tail = q.tile;
                         }
-                        v[i] = ME::Pack(f);  // rows past M / channels past Cin feed accumulator rows/steps nobody reads
+                    }
+                    if (ch0 < p.Cin) {
+                        float sc[EPV], sh[EPV];
+#pragma unroll
+                        for (int e = 0; e < EPV; e += 4) {
+                            float4 a = *reinterpret_cast<const float4*>(s_pre_scale + ch0 + e);
+                            float4 b = *reinterpret_cast<const float4*>(s_pre_shift + ch0 + e);
+                            sc[e] = a.x; sc[e + 1] = a.y; sc[e + 2] = a.z; sc[e + 3] = a.w;
+                            sh[e] = b.x; sh[e + 1] = b.y; sh[e + 2] = b.z; sh[e + 3] = b.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (MODE == kModeGather) {  // zero padding must stay zero: skip out-of-image taps
+                                int iy = (ri_tail.oyx[i] >> 16) + fr;
+                                int ix = (int)(short)(ri_tail.oyx[i] & 0xFFFF) + fs;
+                                if (!(ri_tail.pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)) continue;
+                            }
+                            uint4 v;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a_base + sw_off[i]) : "memory");
+                            float f[EPV];
+                            ME::Unpack(v, f);
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e) {
+                                float t = fmaf(f[e], sc[e], sh[e]);
+                                f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
+                            }
+                            StsV4(a_base + sw_off[i], ME::Pack(f));
+                        }
                     }
                 }
-                MbarWait(&empty_bar[stage], phase ^ 1u);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) StsV4(a_base + sw_off[i], v[i]);
                 FenceProxyAsync();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 MbarArrive(&full_bar[stage]);
             };
-            uint4 v0[8], v1[8];
-            if (cur.tile < num_tiles) {
-                load(cur, v0);
-                for (;;) {
-                    ChunkIter n1 = cur;
-                    n1.Step(2, p.num_chunks);
-                    const bool h1 = n1.tile < num_tiles;
-                    if (h1) load(n1, v1);
-                    process(cur, v0);
-                    if (!h1) break;
-                    ChunkIter n2 = n1;
-                    n2.Step(2, p.num_chunks);
-                    const bool h2 = n2.tile < num_tiles;
-                    if (h2) load(n2, v0);
-                    process(n1, v1);
-                    if (!h2) break;
-                    cur = n2;
-                }
-            }
-        } else if (MODE == kModeGather || MODE == kModeStem) {
-            // ---- cp.async path: up to kDepth chunks per group in flight, no registers held
-            constexpr int kDepth = (NS - 2) / 2;  // 2*kDepth < NS, or the ring would deadlock on its own lag
-            RowInfo ri;
-            int decoded_tile = -1;
-            uint32_t k = 0;  // chunks issued by this group
+
             for (; cur.tile < num_tiles; cur.Step(2, p.num_chunks), ++k) {
-                if (cur.tile != decoded_tile) {
-                    DecodeRows<MODE>(p, cur.tile / p.num_n_tiles, rbase, ri);
-                    decoded_tile = cur.tile;
-                }
                 const int stage = cur.it % NS;
                 const uint32_t phase = (cur.it / NS) & 1u;
                 const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
+                if (MODE != kModeLinear && cur.tile != decoded_tile) {
+                    DecodeRows<MODE>(p, cur.tile / p.num_n_tiles, rbase, ri);
+                    decoded_tile = cur.tile;
+                }
                 MbarWait(&empty_bar[stage], phase ^ 1u);
                 if (MODE == kModeStem) {
                     // chunk c = filter rows 2c, 2c+1; a filter row is 8 pixels x 4 channels (64 B); this thread owns
@@ -484,6 +474,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                         CpAsync8(a_base + sw_off[i], ok0 ? row + (size_t)ix * p.in_pitch : in, ok0);
                         CpAsync8(a_base + sw_off[i] + 8, ok1 ? row + (size_t)(ix + 1) * p.in_pitch : in, ok1);
                     }
+                } else if (MODE == kModeLinear) {
+                    const int m_tile = cur.tile / p.num_n_tiles;
+                    const int ch0 = cur.c * ME::kChunk + sub * EPV;
+                    const bool ch_ok = ch0 < p.Cin;
+                    const MmaT* src0 = in + (size_t)(m_tile * kTileM + rbase) * p.in_pitch + p.in_coff + ch0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = ch_ok && (m_tile * kTileM + rbase + 16 * i) < p.M;
+                        CpAsync16(a_base + sw_off[i], ok ? src0 + (size_t)(16 * i) * p.in_pitch : in, ok);
+                    }
                 } else {
                     const int tap = cur.c / p.chunks_per_tap, j = cur.c - tap * p.chunks_per_tap;
                     const int fr = tap / p.S, fs = tap - fr * p.S;
@@ -499,22 +499,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     }
                 }
                 CpAsyncCommit();
-                if (k >= kDepth) {
+                if (k >= (uint32_t)kDepth) {
                     CpAsyncWait<kDepth>();  // the chunk issued kDepth iterations ago has landed
-                    FenceProxyAsync();
-                    MbarArrive(&full_bar[(cur.it - 2 * kDepth) % NS]);
+                    finish(tail);
+                    tail.Step(2, p.num_chunks);
                 }
             }
             CpAsyncWait<0>();
-            FenceProxyAsync();
-            {
-                // drain: arrive for the last min(k, kDepth) chunks, oldest first
-                uint32_t pending = k < (uint32_t)kDepth ? k : (uint32_t)kDepth;
-                uint32_t last_it = (uint32_t)group + 2u * (k - 1u);
-                for (uint32_t d = pending; d >= 1; --d) MbarArrive(&full_bar[(last_it - 2u * (d - 1u)) % NS]);
-            }
+            for (; tail.it < cur.it; tail.Step(2, p.num_chunks)) finish(tail);
         } else {
-            // ---- register paths with per-row address decode (prologue + window, or 2x2 pooled prologue)
+            // ---- register path: 2x2 average pooling of the prologue-transformed input (transition layers)
             RowInfo ri;
             int decoded_tile = -1;
             for (; cur.tile < num_tiles; cur.Step(2, p.num_chunks)) {
@@ -535,33 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     sc[e] = has_pre ? s_pre_scale[ch0 + e] : 1.f;
                     sh[e] = has_pre ? s_pre_shift[ch0 + e] : 0.f;
                 }
-                if (MODE == kModeGatherPre) {
-                    uint4 v[8];
-                    bool ok[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        int iy = (ri.oyx[i] >> 16) + fr;
-                        int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + fs;
-                        ok[i] = ch_ok && ri.pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                        v[i] = make_uint4(0u, 0u, 0u, 0u);
-                        if (ok[i]) v[i] = LdgNc(in + ((size_t)ri.pix[i] + (size_t)iy * p.W + ix) * p.in_pitch + p.in_coff + ch0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (!ok[i]) continue;  // padding stays exactly zero
-                        float f[EPV];
-                        ME::Unpack(v[i], f);
-#pragma unroll
-                        for (int e = 0; e < EPV; ++e) {
-                            float t = fmaf(f[e], sc[e], sh[e]);
-                            f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
-                        }
-                        v[i] = ME::Pack(f);
-                    }
-                    MbarWait(&empty_bar[stage], phase ^ 1u);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) StsV4(a_base + sw_off[i], v[i]);
-                } else {  // kModePool2: A row = mean of the 2x2 input pixels after the prologue
+                {  // kModePool2: A row = mean of the 2x2 input pixels after the prologue
                     MbarWait(&empty_bar[stage], phase ^ 1u);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -616,7 +584,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             MbarWait(&tmem_full[acc], acc_phase);
             TcFenceAfter();
             const int m = m_tile * kTileM + e * 32 + lane;
-            OutT* orow = out + (size_t)m * p.out_pitch + p.out_coff;
 #pragma unroll 1
             for (int cg = 0; cg < BN / 32; ++cg) {
                 uint32_t r[32];
@@ -638,16 +605,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                         for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.f);
                     }
-                    if (sizeof(OutT) == 2) {
+                    // stage this thread's 32 channels (one row) in shared memory ...
+                    constexpr int kRowB = 32 * (int)sizeof(OutT);       // bytes per row of this column group
+                    constexpr int kPieces = kRowB / 16;                 // 16-byte pieces per row (4 bf16 / 2 e4m3)
+                    constexpr int kPitch = kRowB + 16;                  // padded: conflict-free row-wise writes
+                    const uint32_t st_base = SmemAddr(s_stage + e * (32 * kPitch));
 #pragma unroll
-                        for (int q = 0; q < 32; q += 8)
-                            if (co0 + q < p.Cout) *reinterpret_cast<uint4*>(orow + co0 + q) = MmaElem<__nv_bfloat16>::Pack(f + q);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 32; q += 16)
-                            if (co0 + q < p.Cout) *reinterpret_cast<uint4*>(orow + co0 + q) = MmaElem<__nv_fp8_e4m3>::Pack(f + q);
+                    for (int q = 0; q < kPieces; ++q) {
+                        uint4 w = sizeof(OutT) == 2 ? MmaElem<__nv_bfloat16>::Pack(f + 8 * q) : MmaElem<__nv_fp8_e4m3>::Pack(f + 16 * q);
+                        StsV4(st_base + lane * kPitch + q * 16, w);
                     }
                 }
+                __syncwarp();
+                {
+                    // ... and write it out with kPieces consecutive lanes per row (full 32/64-byte segments per row
+                    // instead of 32 scattered 16-byte stores per instruction)
+                    constexpr int kRowB = 32 * (int)sizeof(OutT);
+                    constexpr int kPieces = kRowB / 16;
+                    constexpr int kPitch = kRowB + 16;
+                    const uint32_t st_base = SmemAddr(s_stage + e * (32 * kPitch));
+                    const int co0 = n_tile * BN + cg * 32;
+#pragma unroll
+                    for (int i = 0; i < kPieces; ++i) {
+                        const int idx = lane + 32 * i;
+                        const int row = idx / kPieces, piece = idx % kPieces;
+                        const int mr = m_tile * kTileM + e * 32 + row;
+                        const int co = co0 + piece * (16 / (int)sizeof(OutT));
+                        if (mr < p.M && co < p.Cout) {
+                            uint4 v;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(st_base + row * kPitch + piece * 16) : "memory");
+                            *reinterpret_cast<uint4*>(out + (size_t)mr * p.out_pitch + p.out_coff + co) = v;
+                        }
+                    }
+                }
+                __syncwarp();
             }
             TcFenceBefore();
             MbarArrive(&tmem_empty[acc]);
@@ -736,7 +727,8 @@ constexpr int kHaloPlaneStride = kHaloPatchPixels * 16 + 16;  // +16 B: planes s
 constexpr int kHaloMaxPieces = 16;                // Cin * esz / 16 <= 16  (128 bf16 or 256 e4m3... capped by Cin<=128)
 constexpr int kHaloPatchBytes = ((kHaloMaxPieces * kHaloPlaneStride + 1023) / 1024) * 1024;
 constexpr int kHaloWeightBytes = 18 * 32 * kRowBytes;  // 9 taps x <=2 chunks x [32][128 B]
-constexpr int kHaloSmemBytes = 1024 + kHaloWeightBytes + 2 * kHaloPatchBytes + 2 * 32 * 4 + 256;
+constexpr int kHaloBufs = 3;  // patch ring: two tiles in flight while one is consumed
+constexpr int kHaloSmemBytes = 1024 + kHaloWeightBytes + kHaloBufs * kHaloPatchBytes + 2 * 32 * 4 + 256;
 
 struct HParams {
     const void* in;
@@ -767,12 +759,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;                                  // resident weights, SW128 K-major tiles of 4 KB
     uint8_t* s_patch = smem + kHaloWeightBytes;           // 2 patch buffers
-    float* s_out_scale = reinterpret_cast<float*>(s_patch + 2 * kHaloPatchBytes);
+    float* s_out_scale = reinterpret_cast<float*>(s_patch + kHaloBufs * kHaloPatchBytes);
     float* s_bias = s_out_scale + 32;
     uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_bias + 32);
     uint64_t* patch_full = w_bar + 1;
-    uint64_t* patch_empty = patch_full + 2;
-    uint64_t* tmem_full = patch_empty + 2;
+    uint64_t* patch_empty = patch_full + kHaloBufs;
+    uint64_t* tmem_full = patch_empty + kHaloBufs;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -782,9 +774,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
 
     if (warp == 12 && lane == 0) {
         MbarInit(w_bar, 1);
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kHaloBufs; ++b) {
             MbarInit(&patch_full[b], 256);
             MbarInit(&patch_empty[b], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
             MbarInit(&tmem_full[b], 1);
             MbarInit(&tmem_empty[b], 128);
         }
@@ -798,7 +792,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     }
     // the slack pixels past the patch are read by junk rows only, but must never hold NaN-producing garbage
     // for rows that ARE stored: they are not (junk rows only); still, clear both buffers once for hygiene
-    for (int i = threadIdx.x; i < 2 * kHaloPatchBytes / 16; i += kThreads)
+    for (int i = threadIdx.x; i < kHaloBufs * kHaloPatchBytes / 16; i += kThreads)
         reinterpret_cast<uint4*>(s_patch)[i] = make_uint4(0u, 0u, 0u, 0u);
     FenceProxyAsync();
     TcFenceBefore();
@@ -811,34 +805,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         const MmaT* in = reinterpret_cast<const MmaT*>(p.in);
         const int tid = threadIdx.x;  // 0..255
         uint32_t k = 0;
+        constexpr int kFullPieces = 128 / EPV;
+        const bool full_c = pieces == kFullPieces;
+        // fixed K piece per thread (256 % pieces == 0): no div/mod in the copy loop
+        const int kp = full_c ? tid % kFullPieces : tid % pieces;
+        const int q0 = full_c ? tid / kFullPieces : tid / pieces;
+        const int qstep = full_c ? 256 / kFullPieces : 256 / pieces;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
-            const int buf = k & 1;
+            const int buf = k % kHaloBufs;
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
             const int iy0 = ty * p.TH - 1, ix0 = tx * p.TW - 1;
-            const int rows = p.TH + 2;
-            const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes);
-            MbarWait(&patch_empty[buf], ((k >> 1) & 1u) ^ 1u);
-            const int total = rows * kHaloPW * pieces;
-            constexpr int kFullPieces = 128 / EPV;
-            for (int e = tid; e < total; e += 256) {
-                const int kp = pieces == kFullPieces ? e % kFullPieces : e % pieces;
-                const int q = pieces == kFullPieces ? e / kFullPieces : e / pieces;
-                const int py = q / kHaloPW, px = q - py * kHaloPW;
-                const int iy = iy0 + py, ix = ix0 + px;
+            const int npix = (p.TH + 2) * kHaloPW;
+            const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes) + kp * kHaloPlaneStride;
+            const MmaT* ibase = in + (size_t)img * p.H * p.W * p.in_pitch + p.in_coff + kp * EPV;
+            MbarWait(&patch_empty[buf], ((k / kHaloBufs) & 1u) ^ 1u);
+            for (int q = q0; q < npix; q += qstep) {
+                const int iy = iy0 + (q >> 4), ix = ix0 + (q & 15);
                 const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                const MmaT* src = ok ? in + ((size_t)(img * p.H + iy) * p.W + ix) * p.in_pitch + p.in_coff + kp * EPV : in;
-                CpAsync16(pbase + kp * kHaloPlaneStride + q * 16, src, ok);
+                CpAsync16(pbase + q * 16, ok ? ibase + ((size_t)iy * p.W + ix) * p.in_pitch : in, ok);
             }
             CpAsyncCommit();
-            if (k >= 1) {
-                CpAsyncWait<1>();  // the previous tile's patch has landed
+            if (k >= (uint32_t)(kHaloBufs - 1)) {
+                CpAsyncWait<kHaloBufs - 1>();  // the patch issued kHaloBufs-1 tiles ago has landed
                 FenceProxyAsync();
-                MbarArrive(&patch_full[(k - 1) & 1]);
+                MbarArrive(&patch_full[(k - (kHaloBufs - 1)) % kHaloBufs]);
             }
         }
         CpAsyncWait<0>();
         FenceProxyAsync();
-        if (k >= 1) MbarArrive(&patch_full[(k - 1) & 1]);
+        {
+            uint32_t pending = k < (uint32_t)(kHaloBufs - 1) ? k : (uint32_t)(kHaloBufs - 1);
+            for (uint32_t d = pending; d >= 1; --d) MbarArrive(&patch_full[(k - d) % kHaloBufs]);
+        }
     } else if (warp < 12) {
         // =========================================================== epilogue
         const int e = warp & 3;
@@ -900,11 +898,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         MbarWait(w_bar, 0);
         uint32_t k = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
-            const uint32_t buf = k & 1u, ph = (k >> 1) & 1u;
-            MbarWait(&tmem_empty[buf], ph ^ 1u);
+            const uint32_t buf = k % kHaloBufs, ph = (k / kHaloBufs) & 1u;
+            const uint32_t acc = k & 1u, acc_ph = (k >> 1) & 1u;
+            MbarWait(&tmem_empty[acc], acc_ph ^ 1u);
             MbarWait(&patch_full[buf], ph);
             TcFenceAfter();
-            const uint32_t d_addr = tmem_u + buf * BN;
+            const uint32_t d_addr = tmem_u + acc * BN;
             const uint64_t a0 = a_base + (uint64_t)(buf * (kHaloPatchBytes >> 4));
             constexpr int CPT = 128 / ME::kChunk;  // chunks per tap when Cin == 128
             if (ElectOne()) {
@@ -941,7 +940,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
                     }
                 }
                 UmmaCommit(&patch_empty[buf]);
-                UmmaCommit(&tmem_full[buf]);
+                UmmaCommit(&tmem_full[acc]);
             }
             __syncwarp();
         }
@@ -1011,7 +1010,6 @@ cudaError_t LaunchMode(int mode, int bn, const CUtensorMap& tm, const UParams& p
     switch (mode) {
         case kModeLinear: return LaunchBN<MmaT, OutT, kModeLinear>(bn, tm, p, stream);
         case kModeGather: return LaunchBN<MmaT, OutT, kModeGather>(bn, tm, p, stream);
-        case kModeGatherPre: return LaunchBN<MmaT, OutT, kModeGatherPre>(bn, tm, p, stream);
         case kModePool2: return LaunchBN<MmaT, OutT, kModePool2>(bn, tm, p, stream);
     }
     return cudaErrorInvalidValue;
@@ -1092,7 +1090,7 @@ cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t strea
     int mode;
     if (a.pool2) mode = kModePool2;
     else if (a.R == 1 && a.S == 1 && a.stride == 1 && a.pad == 0) mode = kModeLinear;
-    else mode = a.pre_scale ? kModeGatherPre : kModeGather;
+    else mode = kModeGather;
     if (it == DType::BF16 && ot == DType::BF16) return LaunchMode<__nv_bfloat16, __nv_bfloat16>(mode, bn, tm, p, stream);
     if (it == DType::FP8 && ot == DType::FP8) return LaunchMode<__nv_fp8_e4m3, __nv_fp8_e4m3>(mode, bn, tm, p, stream);
     return cudaErrorInvalidValue;
