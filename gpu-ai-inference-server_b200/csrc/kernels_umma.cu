@@ -61,6 +61,18 @@ __device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (mbarrier.test_wait never suspends the thread).
+__device__ __forceinline__ bool MbarTest(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(SmemAddr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // A lost arrive must become an error, not a hung GPU: trap after a generous spin budget.
 __device__ __noinline__ void MbarTimeout() {
     printf("conv_umma: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
@@ -394,12 +406,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             // ---- cp.async path: up to kDepth chunks per group in flight with no registers held.  When the layer
             //      has a prologue (folded BN + ReLU) each thread transforms, IN PLACE, exactly the 16-byte pieces
             //      it copied itself once they have landed (so no cross-thread hazard, no extra staging buffer).
-            constexpr int kDepth = (NS - 2) / 2;  // 2*kDepth < NS, or the ring would deadlock on its own lag
+            constexpr int kDepth = 3;  // chunks of this group in flight (the other group adds as many)
             RowInfo ri, ri_tail;
             int decoded_tile = -1, decoded_tail = -1;
             ChunkIter tail = cur;
-            uint32_t k = 0;  // chunks issued by this group
-
             auto finish = [&](const ChunkIter& q) {  // chunk q has landed: optional in-place prologue, then publish
                 const int stage = q.it % NS;
                 if (MODE != kModeStem && has_pre) {
@@ -450,63 +460,77 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 MbarArrive(&full_bar[stage]);
             };
 
-            for (; cur.tile < num_tiles; cur.Step(2, p.num_chunks), ++k) {
-                const int stage = cur.it % NS;
-                const uint32_t phase = (cur.it / NS) & 1u;
-                const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
-                if (MODE != kModeLinear && cur.tile != decoded_tile) {
-                    DecodeRows<MODE>(p, cur.tile / p.num_n_tiles, rbase, ri);
-                    decoded_tile = cur.tile;
-                }
-                MbarWait(&empty_bar[stage], phase ^ 1u);
-                if (MODE == kModeStem) {
-                    // chunk c = filter rows 2c, 2c+1; a filter row is 8 pixels x 4 channels (64 B); this thread owns
-                    // 2 pixels of one filter row: piece = sub & 3, filter row = 2c + (sub >> 2)
-                    const int r = 2 * cur.c + (sub >> 2);
-                    const int dx = 2 * (sub & 3);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        int iy = (ri.oyx[i] >> 16) + r;
-                        int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + dx;
-                        bool rok = ri.pix[i] >= 0 && r < p.R && iy >= 0 && iy < p.H;
-                        bool ok0 = rok && ix >= 0 && ix < p.W, ok1 = rok && ix + 1 >= 0 && ix + 1 < p.W;
-                        const MmaT* row = in + ((size_t)(rok ? ri.pix[i] : 0) + (size_t)(rok ? iy : 0) * p.W) * p.in_pitch;
-                        CpAsync8(a_base + sw_off[i], ok0 ? row + (size_t)ix * p.in_pitch : in, ok0);
-                        CpAsync8(a_base + sw_off[i] + 8, ok1 ? row + (size_t)(ix + 1) * p.in_pitch : in, ok1);
+            // Adaptive ring: issue while a stage is free and fewer than kDepth chunks of this group are in flight;
+            // otherwise retire (publish) the oldest landed chunk.  Publishing never waits on stage availability.
+            int in_flight = 0;
+            for (;;) {
+                if (cur.tile < num_tiles && in_flight < kDepth) {
+                    const int stage = cur.it % NS;
+                    const uint32_t phase = (cur.it / NS) & 1u;
+                    bool free_slot = MbarTest(&empty_bar[stage], phase ^ 1u);
+                    if (!free_slot && in_flight == 0) {
+                        MbarWait(&empty_bar[stage], phase ^ 1u);
+                        free_slot = true;
                     }
-                } else if (MODE == kModeLinear) {
-                    const int m_tile = cur.tile / p.num_n_tiles;
-                    const int ch0 = cur.c * ME::kChunk + sub * EPV;
-                    const bool ch_ok = ch0 < p.Cin;
-                    const MmaT* src0 = in + (size_t)(m_tile * kTileM + rbase) * p.in_pitch + p.in_coff + ch0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool ok = ch_ok && (m_tile * kTileM + rbase + 16 * i) < p.M;
-                        CpAsync16(a_base + sw_off[i], ok ? src0 + (size_t)(16 * i) * p.in_pitch : in, ok);
-                    }
-                } else {
-                    const int tap = cur.c / p.chunks_per_tap, j = cur.c - tap * p.chunks_per_tap;
-                    const int fr = tap / p.S, fs = tap - fr * p.S;
-                    const int ch0 = j * ME::kChunk + sub * EPV;
-                    const bool ch_ok = ch0 < p.Cin;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        int iy = (ri.oyx[i] >> 16) + fr;
-                        int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + fs;
-                        bool ok = ch_ok && ri.pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                        const MmaT* src = ok ? in + ((size_t)ri.pix[i] + (size_t)iy * p.W + ix) * p.in_pitch + p.in_coff + ch0 : in;
-                        CpAsync16(a_base + sw_off[i], src, ok);  // src-size 0 => 16 bytes of zeros (padding)
+                    if (free_slot) {
+                        const uint32_t a_base = SmemAddr(smem + stage * Cfg::kStageBytes);
+                        if (MODE != kModeLinear && cur.tile != decoded_tile) {
+                            DecodeRows<MODE>(p, cur.tile / p.num_n_tiles, rbase, ri);
+                            decoded_tile = cur.tile;
+                        }
+                        if (MODE == kModeStem) {
+                            // chunk c = filter rows 2c, 2c+1; a filter row is 8 pixels x 4 channels (64 B); this thread owns
+                            // 2 pixels of one filter row: piece = sub & 3, filter row = 2c + (sub >> 2)
+                            const int r = 2 * cur.c + (sub >> 2);
+                            const int dx = 2 * (sub & 3);
+        #pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                int iy = (ri.oyx[i] >> 16) + r;
+                                int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + dx;
+                                bool rok = ri.pix[i] >= 0 && r < p.R && iy >= 0 && iy < p.H;
+                                bool ok0 = rok && ix >= 0 && ix < p.W, ok1 = rok && ix + 1 >= 0 && ix + 1 < p.W;
+                                const MmaT* row = in + ((size_t)(rok ? ri.pix[i] : 0) + (size_t)(rok ? iy : 0) * p.W) * p.in_pitch;
+                                CpAsync8(a_base + sw_off[i], ok0 ? row + (size_t)ix * p.in_pitch : in, ok0);
+                                CpAsync8(a_base + sw_off[i] + 8, ok1 ? row + (size_t)(ix + 1) * p.in_pitch : in, ok1);
+                            }
+                        } else if (MODE == kModeLinear) {
+                            const int m_tile = cur.tile / p.num_n_tiles;
+                            const int ch0 = cur.c * ME::kChunk + sub * EPV;
+                            const bool ch_ok = ch0 < p.Cin;
+                            const MmaT* src0 = in + (size_t)(m_tile * kTileM + rbase) * p.in_pitch + p.in_coff + ch0;
+        #pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const bool ok = ch_ok && (m_tile * kTileM + rbase + 16 * i) < p.M;
+                                CpAsync16(a_base + sw_off[i], ok ? src0 + (size_t)(16 * i) * p.in_pitch : in, ok);
+                            }
+                        } else {
+                            const int tap = cur.c / p.chunks_per_tap, j = cur.c - tap * p.chunks_per_tap;
+                            const int fr = tap / p.S, fs = tap - fr * p.S;
+                            const int ch0 = j * ME::kChunk + sub * EPV;
+                            const bool ch_ok = ch0 < p.Cin;
+        #pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                int iy = (ri.oyx[i] >> 16) + fr;
+                                int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + fs;
+                                bool ok = ch_ok && ri.pix[i] >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                                const MmaT* src = ok ? in + ((size_t)ri.pix[i] + (size_t)iy * p.W + ix) * p.in_pitch + p.in_coff + ch0 : in;
+                                CpAsync16(a_base + sw_off[i], src, ok);  // src-size 0 => 16 bytes of zeros (padding)
+                            }
+                        }
+                        CpAsyncCommit();
+                        ++in_flight;
+                        cur.Step(2, p.num_chunks);
+                        continue;
                     }
                 }
-                CpAsyncCommit();
-                if (k >= (uint32_t)kDepth) {
-                    CpAsyncWait<kDepth>();  // the chunk issued kDepth iterations ago has landed
-                    finish(tail);
-                    tail.Step(2, p.num_chunks);
-                }
+                if (in_flight == 0) break;
+                if (in_flight == 1) CpAsyncWait<0>();
+                else if (in_flight == 2) CpAsyncWait<1>();
+                else CpAsyncWait<2>();
+                finish(tail);
+                tail.Step(2, p.num_chunks);
+                --in_flight;
             }
-            CpAsyncWait<0>();
-            for (; tail.it < cur.it; tail.Step(2, p.num_chunks)) finish(tail);
         } else {
             // ---- register path: 2x2 average pooling of the prologue-transformed input (transition layers)
             RowInfo ri;
@@ -811,31 +835,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
         const int kp = full_c ? tid % kFullPieces : tid % pieces;
         const int q0 = full_c ? tid / kFullPieces : tid / pieces;
         const int qstep = full_c ? 256 / kFullPieces : 256 / pieces;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
-            const int buf = k % kHaloBufs;
-            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
-            const int iy0 = ty * p.TH - 1, ix0 = tx * p.TW - 1;
-            const int npix = (p.TH + 2) * kHaloPW;
-            const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes) + kp * kHaloPlaneStride;
-            const MmaT* ibase = in + (size_t)img * p.H * p.W * p.in_pitch + p.in_coff + kp * EPV;
-            MbarWait(&patch_empty[buf], ((k / kHaloBufs) & 1u) ^ 1u);
-            for (int q = q0; q < npix; q += qstep) {
-                const int iy = iy0 + (q >> 4), ix = ix0 + (q & 15);
-                const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                CpAsync16(pbase + q * 16, ok ? ibase + ((size_t)iy * p.W + ix) * p.in_pitch : in, ok);
+        // Adaptive ring (see the main kernel): issue while a patch buffer is free and < kHaloBufs-1 tiles are in
+        // flight, otherwise publish the oldest landed patch.
+        int tile = blockIdx.x;
+        uint32_t done = 0;  // patches published
+        int in_flight = 0;
+        for (;;) {
+            if (tile < p.num_tiles && in_flight < kHaloBufs - 1) {
+                const int buf = k % kHaloBufs;
+                const uint32_t par = ((k / kHaloBufs) & 1u) ^ 1u;
+                bool free_buf = MbarTest(&patch_empty[buf], par);
+                if (!free_buf && in_flight == 0) {
+                    MbarWait(&patch_empty[buf], par);
+                    free_buf = true;
+                }
+                if (free_buf) {
+                    const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+                    const int iy0 = ty * p.TH - 1, ix0 = tx * p.TW - 1;
+                    const int npix = (p.TH + 2) * kHaloPW;
+                    const uint32_t pbase = SmemAddr(s_patch + buf * kHaloPatchBytes) + kp * kHaloPlaneStride;
+                    const MmaT* ibase = in + (size_t)img * p.H * p.W * p.in_pitch + p.in_coff + kp * EPV;
+                    for (int q = q0; q < npix; q += qstep) {
+                        const int iy = iy0 + (q >> 4), ix = ix0 + (q & 15);
+                        const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                        CpAsync16(pbase + q * 16, ok ? ibase + ((size_t)iy * p.W + ix) * p.in_pitch : in, ok);
+                    }
+                    CpAsyncCommit();
+                    ++in_flight;
+                    ++k;
+                    tile += gridDim.x;
+                    continue;
+                }
             }
-            CpAsyncCommit();
-            if (k >= (uint32_t)(kHaloBufs - 1)) {
-                CpAsyncWait<kHaloBufs - 1>();  // the patch issued kHaloBufs-1 tiles ago has landed
-                FenceProxyAsync();
-                MbarArrive(&patch_full[(k - (kHaloBufs - 1)) % kHaloBufs]);
-            }
-        }
-        CpAsyncWait<0>();
-        FenceProxyAsync();
-        {
-            uint32_t pending = k < (uint32_t)(kHaloBufs - 1) ? k : (uint32_t)(kHaloBufs - 1);
-            for (uint32_t d = pending; d >= 1; --d) MbarArrive(&patch_full[(k - d) % kHaloBufs]);
+            if (in_flight == 0) break;
+            if (in_flight == 1) CpAsyncWait<0>();
+            else CpAsyncWait<1>();
+            FenceProxyAsync();
+            MbarArrive(&patch_full[done % kHaloBufs]);
+            ++done;
+            --in_flight;
         }
     } else if (warp < 12) {
         // =========================================================== epilogue
