@@ -242,6 +242,64 @@ template <> struct MmaElem<__nv_fp8_e4m3> {
     }
 };
 
+// ------------------------------------------------------------------ packed prologue math
+// Folded BatchNorm (+ReLU) on packed pairs: one fma.rn[.relu] per two channels.
+template <bool RELU> __device__ __forceinline__ uint32_t FmaBf16x2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    if (RELU) asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <bool RELU> __device__ __forceinline__ uint32_t FmaF16x2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    if (RELU) asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    else asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t E4m3x2ToF16x2(uint32_t v16) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(d) : "h"((unsigned short)v16));
+    return d;
+}
+__device__ __forceinline__ uint32_t F16x2ToE4m3x2(uint32_t v) {
+    unsigned short d;
+    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(d) : "r"(v));
+    return (uint32_t)d;
+}
+// Packs two fp32 per-channel constants for the packed prologue of each MMA element type.
+template <typename T> __device__ __forceinline__ uint32_t PackPair(float a, float b);
+template <> __device__ __forceinline__ uint32_t PackPair<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t PackPair<__nv_fp8_e4m3>(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+// y = [relu](x * scale + shift) on one 16-byte piece; sc/sh hold one packed pair per two channels.
+template <typename T, bool RELU> __device__ __forceinline__ uint4 ProloguePiece(uint4 v, const uint32_t* sc, const uint32_t* sh);
+template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_bfloat16, true>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(FmaBf16x2<true>(v.x, sc[0], sh[0]), FmaBf16x2<true>(v.y, sc[1], sh[1]),
+                      FmaBf16x2<true>(v.z, sc[2], sh[2]), FmaBf16x2<true>(v.w, sc[3], sh[3]));
+}
+template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_bfloat16, false>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(FmaBf16x2<false>(v.x, sc[0], sh[0]), FmaBf16x2<false>(v.y, sc[1], sh[1]),
+                      FmaBf16x2<false>(v.z, sc[2], sh[2]), FmaBf16x2<false>(v.w, sc[3], sh[3]));
+}
+template <bool RELU> __device__ __forceinline__ uint32_t PrologueWordFp8(uint32_t w, const uint32_t* sc, const uint32_t* sh) {
+    uint32_t lo = FmaF16x2<RELU>(E4m3x2ToF16x2(w & 0xFFFFu), sc[0], sh[0]);
+    uint32_t hi = FmaF16x2<RELU>(E4m3x2ToF16x2(w >> 16), sc[1], sh[1]);
+    return F16x2ToE4m3x2(lo) | (F16x2ToE4m3x2(hi) << 16);
+}
+template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_fp8_e4m3, true>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(PrologueWordFp8<true>(v.x, sc, sh), PrologueWordFp8<true>(v.y, sc + 2, sh + 2),
+                      PrologueWordFp8<true>(v.z, sc + 4, sh + 4), PrologueWordFp8<true>(v.w, sc + 6, sh + 6));
+}
+template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_fp8_e4m3, false>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(PrologueWordFp8<false>(v.x, sc, sh), PrologueWordFp8<false>(v.y, sc + 2, sh + 2),
+                      PrologueWordFp8<false>(v.z, sc + 4, sh + 4), PrologueWordFp8<false>(v.w, sc + 6, sh + 6));
+}
+
 struct UParams {
     const void* in;
     void* out;
@@ -322,10 +380,22 @@ __device__ __forceinline__ void DecodeRows(const UParams& p, int m_tile, int rba
             int ox = m % p.Wo, oy = (m / p.Wo) % p.Ho, img = m / (p.Wo * p.Ho);
             int iy0 = (MODE == kModePool2) ? oy * 2 : oy * p.stride - p.pad;
             int ix0 = (MODE == kModePool2) ? ox * 2 : ox * p.stride - p.pad;
-            ri.pix[i] = img * p.H * p.W;
-            ri.oyx[i] = (int)(((unsigned)iy0 << 16) | ((unsigned)ix0 & 0xFFFFu));
+            if (MODE == kModeStem) {
+                // pix = element offset of the receptive field's top-left pixel (may point before the image);
+                // oyx = validity masks: bit 8+r <=> filter row r is inside the image, bit d <=> column ix0+d is
+                ri.pix[i] = ((img * p.H + iy0) * p.W + ix0) * p.in_pitch;
+                uint32_t ymask = 0, xmask = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) ymask |= (uint32_t)(r < p.R && iy0 + r >= 0 && iy0 + r < p.H) << r;
+#pragma unroll
+                for (int d = 0; d < 8; ++d) xmask |= (uint32_t)(d < p.S && ix0 + d >= 0 && ix0 + d < p.W) << d;
+                ri.oyx[i] = (int)((ymask << 8) | xmask);
+            } else {
+                ri.pix[i] = img * p.H * p.W;
+                ri.oyx[i] = (int)(((unsigned)iy0 << 16) | ((unsigned)ix0 & 0xFFFFu));
+            }
         } else {
-            ri.pix[i] = -1;
+            ri.pix[i] = (MODE == kModeStem) ? 0 : -1;
             ri.oyx[i] = 0;
         }
     }
@@ -371,9 +441,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (warp == 13) TmemAlloc(tmem_slot, Cfg::kTmemCols);
     // per-channel vectors -> shared memory (read as broadcasts by the producers / the epilogue)
     if (p.pre_scale) {
-        for (int i = threadIdx.x; i < p.cin_pad; i += kThreads) {
-            s_pre_scale[i] = i < p.Cin ? p.pre_scale[i] : 0.f;
-            s_pre_shift[i] = i < p.Cin ? p.pre_shift[i] : 0.f;
+        if (MODE == kModePool2) {  // fp32 math (four pixels are summed)
+            for (int i = threadIdx.x; i < p.cin_pad; i += kThreads) {
+                s_pre_scale[i] = i < p.Cin ? p.pre_scale[i] : 0.f;
+                s_pre_shift[i] = i < p.Cin ? p.pre_shift[i] : 0.f;
+            }
+        } else {  // packed pairs in the prologue's arithmetic type (bf16x2 / f16x2)
+            uint32_t* sc = reinterpret_cast<uint32_t*>(s_pre_scale);
+            uint32_t* sh = reinterpret_cast<uint32_t*>(s_pre_shift);
+            for (int i = threadIdx.x; i < p.cin_pad / 2; i += kThreads) {
+                const int c0 = 2 * i, c1 = 2 * i + 1;
+                sc[i] = PackPair<MmaT>(c0 < p.Cin ? p.pre_scale[c0] : 0.f, c1 < p.Cin ? p.pre_scale[c1] : 0.f);
+                sh[i] = PackPair<MmaT>(c0 < p.Cin ? p.pre_shift[c0] : 0.f, c1 < p.Cin ? p.pre_shift[c1] : 0.f);
+            }
         }
     }
     for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
@@ -428,11 +508,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                         }
                     }
                     if (ch0 < p.Cin) {
-                        float sc[EPV], sh[EPV];
+                        constexpr int kPairs = EPV / 2;  // packed constants per 16-byte piece
+                        uint32_t sc[kPairs], sh[kPairs];
 #pragma unroll
-                        for (int e = 0; e < EPV; e += 4) {
-                            float4 a = *reinterpret_cast<const float4*>(s_pre_scale + ch0 + e);
-                            float4 b = *reinterpret_cast<const float4*>(s_pre_shift + ch0 + e);
+                        for (int e = 0; e < kPairs; e += 4) {
+                            uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(s_pre_scale) + ch0 / 2 + e);
+                            uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(s_pre_shift) + ch0 / 2 + e);
                             sc[e] = a.x; sc[e + 1] = a.y; sc[e + 2] = a.z; sc[e + 3] = a.w;
                             sh[e] = b.x; sh[e + 1] = b.y; sh[e + 2] = b.z; sh[e + 3] = b.w;
                         }
@@ -445,14 +526,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                             }
                             uint4 v;
                             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a_base + sw_off[i]) : "memory");
-                            float f[EPV];
-                            ME::Unpack(v, f);
-#pragma unroll
-                            for (int e = 0; e < EPV; ++e) {
-                                float t = fmaf(f[e], sc[e], sh[e]);
-                                f[e] = p.pre_relu ? fmaxf(t, 0.f) : t;
-                            }
-                            StsV4(a_base + sw_off[i], ME::Pack(f));
+                            v = p.pre_relu ? ProloguePiece<MmaT, true>(v, sc, sh) : ProloguePiece<MmaT, false>(v, sc, sh);
+                            StsV4(a_base + sw_off[i], v);
                         }
                     }
                 }
@@ -483,15 +558,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                             // 2 pixels of one filter row: piece = sub & 3, filter row = 2c + (sub >> 2)
                             const int r = 2 * cur.c + (sub >> 2);
                             const int dx = 2 * (sub & 3);
-        #pragma unroll
+                            const int off = (r * p.W + dx) * p.in_pitch;
+#pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                int iy = (ri.oyx[i] >> 16) + r;
-                                int ix = (int)(short)(ri.oyx[i] & 0xFFFF) + dx;
-                                bool rok = ri.pix[i] >= 0 && r < p.R && iy >= 0 && iy < p.H;
-                                bool ok0 = rok && ix >= 0 && ix < p.W, ok1 = rok && ix + 1 >= 0 && ix + 1 < p.W;
-                                const MmaT* row = in + ((size_t)(rok ? ri.pix[i] : 0) + (size_t)(rok ? iy : 0) * p.W) * p.in_pitch;
-                                CpAsync8(a_base + sw_off[i], ok0 ? row + (size_t)ix * p.in_pitch : in, ok0);
-                                CpAsync8(a_base + sw_off[i] + 8, ok1 ? row + (size_t)(ix + 1) * p.in_pitch : in, ok1);
+                                const uint32_t mk = (uint32_t)ri.oyx[i];
+                                const bool rok = (mk >> (8 + r)) & 1u;
+                                const bool ok0 = rok && ((mk >> dx) & 1u), ok1 = rok && ((mk >> (dx + 1)) & 1u);
+                                const MmaT* src = in + (ri.pix[i] + off);
+                                CpAsync8(a_base + sw_off[i], ok0 ? src : in, ok0);
+                                CpAsync8(a_base + sw_off[i] + 8, ok1 ? src + p.in_pitch : in, ok1);
                             }
                         } else if (MODE == kModeLinear) {
                             const int m_tile = cur.tile / p.num_n_tiles;
