@@ -122,17 +122,24 @@ def _dist():
     import torch.distributed as dist
     rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", os.environ["RANK"]))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    backend = os.environ.get("B200_BENCH_BACKEND", "nccl")  # "gloo" for the CPU-only tests of this plumbing
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dev = f"cuda:{local}"
+    else:
+        dist.init_process_group(backend)
+        dev = "cpu"
 
     def reduce_max(v: float) -> float:
-        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def barrier():
         dist.barrier()
-        torch.cuda.synchronize()
+        if dev != "cpu":
+            torch.cuda.synchronize()
 
     return rank, local, world, reduce_max, barrier
 

@@ -105,7 +105,7 @@ EXPORTED_SYMBOLS = [
     "ModelFreeStats", "ModelLoad", "ModelUnload", "FreeErrorMessage", "GetModelHandle",
 ]
 EXTENSION_SYMBOLS = [
-    "B200EngineVersion", "B200PlanDescribe", "B200KernelLaunchCount", "B200ModelStageInput", "B200ModelForwardDevice",
+    "B200EngineVersion", "B200PlanDescribe", "B200PlanShards", "B200KernelLaunchCount", "B200ModelStageInput", "B200ModelForwardDevice",
     "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue",
 ]
 
@@ -141,6 +141,7 @@ def load_library() -> C.CDLL:
         "FreeErrorMessage": (None, [vp]), "GetModelHandle": (vp, [vp, cp, cp, err]),
         "B200EngineVersion": (cp, []), "B200PlanDescribe": (vp, [cp, cp, i, err]),
         "B200KernelLaunchCount": (C.c_uint64, []),
+        "B200PlanShards": (i, [i, i, i, i, i, C.POINTER(i), i]),
         "B200ModelStageInput": (b, [vp, C.POINTER(CTensorData), err]),
         "B200ModelForwardDevice": (b, [vp, i, i, i, C.POINTER(C.c_float), err]),
         "B200ModelReadOutput": (b, [vp, C.POINTER(C.c_float), sz, err]),
@@ -203,6 +204,14 @@ def engine_version() -> str:
 
 def kernel_launch_count() -> int:
     return int(load_library().B200KernelLaunchCount())
+
+
+def plan_shards(n: int, gpus: int, max_batch: int = 256, min_shard: int = 8, round_robin: int = 0):
+    """(replica, offset, count) triples of the multi-GPU batch scheduler (pure host logic)."""
+    cap = 4096
+    buf = (C.c_int * (3 * cap))()
+    k = load_library().B200PlanShards(n, gpus, max_batch, min_shard, round_robin, buf, cap)
+    return [(buf[3 * j], buf[3 * j + 1], buf[3 * j + 2]) for j in range(min(k, cap))]
 
 
 def plan_describe(model_dir: str, precision: str = "fp32", max_batch: int = 256) -> dict:

@@ -51,6 +51,16 @@ char* B200PlanDescribe(const char* model_dir, const char* precision, int max_bat
     }
 }
 
+int B200PlanShards(int n, int gpus, int max_batch, int min_shard, int round_robin, int* triples, int capacity) {
+    std::vector<inference::ShardPlan> v = inference::PlanShards(n, gpus, max_batch, min_shard, round_robin);
+    for (size_t i = 0; i < v.size() && (int)i < capacity; ++i) {
+        triples[3 * i] = v[i].replica;
+        triples[3 * i + 1] = v[i].off;
+        triples[3 * i + 2] = v[i].cnt;
+    }
+    return (int)v.size();
+}
+
 uint64_t B200KernelLaunchCount(void) { return b200::kernels::LaunchCount(); }
 
 bool B200ModelStageInput(ModelHandle handle, const TensorData* input, ErrorMessage* error) {

@@ -446,6 +446,29 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
     return ok;
 }
 
+// Shard planner (pure function, unit-tested on CPU through B200PlanShards): contiguous split of `n` samples
+// over min(G, n / min_shard) replicas, each shard cut into arena-sized chunks; batches too small to split go
+// to the single replica `round_robin` so that concurrent small requests spread over the GPUs.
+std::vector<ShardPlan> PlanShards(int n, int G, int max_batch, int min_shard, int round_robin) {
+    std::vector<ShardPlan> shards;
+    if (n <= 0 || G <= 0) return shards;
+    max_batch = std::max(1, max_batch);
+    min_shard = std::max(1, min_shard);
+    int use = std::min(G, std::max(1, n / min_shard));
+    if (use <= 1) {
+        int r = ((round_robin % G) + G) % G;
+        for (int off = 0; off < n; off += max_batch) shards.push_back({r, off, std::min(max_batch, n - off)});
+        return shards;
+    }
+    int base = n / use, rem = n % use, off = 0;
+    for (int g = 0; g < use; ++g) {
+        int cnt = base + (g < rem ? 1 : 0);
+        for (int o = 0; o < cnt; o += max_batch) shards.push_back({g, off + o, std::min(max_batch, cnt - o)});
+        off += cnt;
+    }
+    return shards;
+}
+
 // The multi-GPU batch scheduler: contiguous split of the batch over replicas, no collective
 // (SURVEY.md §8e).  Small batches go to one replica chosen round-robin so concurrent callers spread.
 bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs) {
@@ -469,19 +492,14 @@ bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_pt
         outs[i].produced = (size_t)n * out_stride[i];
     }
     static const int kMinShard = std::max(1, atoi(EnvOr("B200_ENGINE_MIN_SHARD", "8").c_str()));
-    struct Shard { int replica, off, cnt; };
-    std::vector<Shard> shards;
-    int use = std::min(G, std::max(1, n / kMinShard));
-    if (use <= 1) {
-        int r = (int)(round_robin_.fetch_add(1) % (unsigned)G);
-        for (int off = 0; off < n; off += max_b) shards.push_back({r, off, std::min(max_b, n - off)});
-    } else {
-        int base = n / use, rem = n % use, off = 0;
-        for (int g = 0; g < use; ++g) {
-            int cnt = base + (g < rem ? 1 : 0);
-            for (int o = 0; o < cnt; o += max_b) shards.push_back({g, off + o, std::min(max_b, cnt - o)});
-            off += cnt;
-        }
+    using Shard = ShardPlan;
+    int rr = (int)(round_robin_.fetch_add(1) % (unsigned)G);
+    std::vector<Shard> shards = PlanShards(n, G, max_b, kMinShard, rr);
+    int use = 0;  // replicas 0..use-1 take part when the batch is split
+    bool single = true;
+    for (auto& s : shards) {
+        use = std::max(use, s.replica + 1);
+        single = single && s.replica == shards[0].replica;
     }
     auto run_shard = [&](const Shard& s) {
         std::vector<const void*> ip(P.inputs.size());
@@ -496,7 +514,7 @@ bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_pt
         }
         st.replicas[s.replica]->Run(s.cnt, ip, op, cap);
     };
-    if (use <= 1) {
+    if (single) {
         for (auto& s : shards) run_shard(s);
         return true;
     }

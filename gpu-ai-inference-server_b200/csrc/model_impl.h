@@ -29,6 +29,12 @@ struct OutDesc {
     size_t produced = 0;        // bytes the engine produced for this output
 };
 
+// One contiguous piece of a batch assigned to one GPU replica.
+struct ShardPlan {
+    int replica, off, cnt;
+};
+std::vector<ShardPlan> PlanShards(int n, int G, int max_batch, int min_shard, int round_robin);
+
 class ModelImpl {
 public:
     ModelImpl(const std::string& model_path, ModelType type, const ModelConfig& config, DeviceType device, int device_id);

@@ -27,6 +27,11 @@ const char* B200EngineVersion(void);
  * per image).  NULL + *error on failure.  Caller frees with free(). */
 char* B200PlanDescribe(const char* model_dir, const char* precision, int max_batch, ErrorMessage* error);
 
+/* The multi-GPU batch scheduler's shard plan as a pure function (no CUDA): how `n` samples are split over
+ * `gpus` replicas with an arena of `max_batch` samples each.  Writes up to `capacity` (replica, offset, count)
+ * triples and returns the number of shards. */
+int B200PlanShards(int n, int gpus, int max_batch, int min_shard, int round_robin, int* triples, int capacity);
+
 /* Number of kernels this library has launched in this process since load (all streams/devices). */
 uint64_t B200KernelLaunchCount(void);
 
