@@ -174,11 +174,11 @@ def run_reference(args):
     ge.ensure_fixtures()
     sample = 16  # images per step: a bounded sample of the 256-image batch
     for _ in range(args.warmup):
-        cpu_oracle_throughput(sample, sample)
+        cpu_oracle_throughput(sample, sample, threads=os.cpu_count())
     per = []
     cores = 0
     for _ in range(args.steps):
-        ips, cores, done, dt = cpu_oracle_throughput(sample, sample)
+        ips, cores, done, dt = cpu_oracle_throughput(sample, sample, threads=os.cpu_count())
         per.append(dt)
     value = sample * len(per) / sum(per)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -307,7 +307,7 @@ def main():
             lat = {"error": repr(e)}
         cpu = None
         if not args.no_cpu_baseline:
-            ips, cores, done, dt = cpu_oracle_throughput(96, 32)
+            ips, cores, done, dt = cpu_oracle_throughput(96, 32, threads=os.cpu_count())  # torchrun pins OMP to 1
             cpu = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{done} images of the same workload in {dt:.1f}s; oracle graph interpreter on torch-CPU "
                              f"(stand-in for ORT-CPU 1.21.0, which cannot be installed here)"}

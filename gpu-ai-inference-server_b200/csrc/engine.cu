@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -73,6 +74,10 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
                         std::to_string(prop.minor) + ") is not a Blackwell sm_100 GPU; this engine ships sm_100a code only");
     }
     CudaCheck(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    CudaCheck(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+    copy_events_.resize(32);
+    for (auto& e : copy_events_) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    if (const char* pc = getenv("B200_ENGINE_PIPELINE_CHUNK")) pipeline_chunk_ = atoi(pc);
     CudaCheck(cudaEventCreate(&ev0_), "cudaEventCreate");
     CudaCheck(cudaEventCreate(&ev1_), "cudaEventCreate");
     CudaCheck(cudaMalloc((void**)&arena_, plan_->arena_bytes + 4096), "cudaMalloc(arena)");
@@ -92,9 +97,13 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
     for (size_t i = 0; i < P.steps.size(); ++i) {
         const Step& s = P.steps[i];
         Prepared& pr = prepared_[i];
-        if (s.in >= 0) pr.in = MakeView(s.in);
-        if (s.in2 >= 0) pr.in2 = MakeView(s.in2);
-        if (s.out >= 0) pr.out = MakeView(s.out);
+        auto io_stride = [&](int tensor) -> size_t {
+            const BufferDesc& b = P.buffers[P.tensors[tensor].buffer];
+            return b.role == BufferDesc::Role::Arena ? 0 : b.BytesPerSample();
+        };
+        if (s.in >= 0) { pr.in = MakeView(s.in); pr.in_io_stride = io_stride(s.in); }
+        if (s.in2 >= 0) { pr.in2 = MakeView(s.in2); pr.in2_io_stride = io_stride(s.in2); }
+        if (s.out >= 0) { pr.out = MakeView(s.out); pr.out_io_stride = io_stride(s.out); }
         pr.scale = vec(s.bn_scale);
         pr.shift = vec(s.bn_shift);
         if (s.kind != StepKind::Conv) continue;
@@ -187,6 +196,8 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
 Replica::~Replica() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
+    if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
+    for (auto& e : copy_events_) if (e) cudaEventDestroy(e);
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
     for (auto& pr : prepared_)
         if (pr.umma.tensor_map) delete (CUtensorMap*)pr.umma.tensor_map;
@@ -222,48 +233,56 @@ kernels::View Replica::MakeView(int tensor) const {
     return v;
 }
 
-void Replica::EnqueueStep(size_t i, int n) {
+void Replica::EnqueueStep(size_t i, int n, int off) {
     const Step& s = plan_->steps[i];
-    Prepared& pr = prepared_[i];
+    const Prepared& pr0 = prepared_[i];
+    // views of graph inputs/outputs are indexed by the sub-batch offset; everything else is scratch
+    kernels::View vin = pr0.in, vin2 = pr0.in2, vout = pr0.out;
+    if (off) {
+        if (vin.base) vin.base = (char*)vin.base + (size_t)off * pr0.in_io_stride;
+        if (vin2.base) vin2.base = (char*)vin2.base + (size_t)off * pr0.in2_io_stride;
+        if (vout.base) vout.base = (char*)vout.base + (size_t)off * pr0.out_io_stride;
+    }
     cudaError_t e = cudaSuccess;
     switch (s.kind) {
-        case StepKind::NchwToNhwc: e = kernels::NchwToNhwc((const float*)pr.in.base, pr.out, n, stream_); break;
-        case StepKind::NhwcToNchw: e = kernels::NhwcToNchw(pr.in, (float*)pr.out.base, n, stream_); break;
+        case StepKind::NchwToNhwc: e = kernels::NchwToNhwc((const float*)vin.base, vout, n, stream_); break;
+        case StepKind::NhwcToNchw: e = kernels::NhwcToNchw(vin, (float*)vout.base, n, stream_); break;
         case StepKind::Conv: {
-            kernels::ConvArgs a = pr.conv;
+            kernels::ConvArgs a = pr0.conv;
+            a.in = vin;
+            a.out = vout;
             a.n = n;
-            e = pr.use_umma ? kernels::ConvUmma(a, pr.umma, stream_) : kernels::ConvSimtF32(a, pr.w_kn, stream_);
+            e = pr0.use_umma ? kernels::ConvUmma(a, pr0.umma, stream_) : kernels::ConvSimtF32(a, pr0.w_kn, stream_);
             break;
         }
-        case StepKind::MaxPool: e = kernels::MaxPool(pr.in, pr.out, n, s.R, s.stride, s.pad, stream_); break;
-        case StepKind::AvgPool: e = kernels::AvgPool(pr.in, pr.out, n, s.R, s.stride, s.pad, s.count_include_pad, stream_); break;
-        case StepKind::BnRelu: e = kernels::BnRelu(pr.in, pr.out, n, pr.scale, pr.shift, s.relu, stream_); break;
+        case StepKind::MaxPool: e = kernels::MaxPool(vin, vout, n, s.R, s.stride, s.pad, stream_); break;
+        case StepKind::AvgPool: e = kernels::AvgPool(vin, vout, n, s.R, s.stride, s.pad, s.count_include_pad, stream_); break;
+        case StepKind::BnRelu: e = kernels::BnRelu(vin, vout, n, pr0.scale, pr0.shift, s.relu, stream_); break;
         case StepKind::GlobalAvgPool:
-            e = kernels::GlobalAvgPool(pr.in, (float*)pr.out.base + pr.out.c_off, pr.out.pitch, n, pr.scale, pr.shift, s.relu, stream_);
+            e = kernels::GlobalAvgPool(vin, (float*)vout.base + vout.c_off, vout.pitch, n, pr0.scale, pr0.shift, s.relu, stream_);
             break;
-        case StepKind::Add: e = kernels::AddTensors(pr.in, pr.in2, pr.out, n, stream_); break;
-        case StepKind::Relu: e = kernels::ReluTensor(pr.in, pr.out, n, stream_); break;
-        case StepKind::Softmax:
-            e = kernels::SoftmaxRows((const float*)pr.in.base, (float*)pr.out.base, n, pr.in.C, stream_);
-            break;
-        case StepKind::CopyChannels: e = kernels::CopyChannels(pr.in, pr.out, n, stream_); break;
+        case StepKind::Add: e = kernels::AddTensors(vin, vin2, vout, n, stream_); break;
+        case StepKind::Relu: e = kernels::ReluTensor(vin, vout, n, stream_); break;
+        case StepKind::Softmax: e = kernels::SoftmaxRows((const float*)vin.base, (float*)vout.base, n, vin.C, stream_); break;
+        case StepKind::CopyChannels: e = kernels::CopyChannels(vin, vout, n, stream_); break;
     }
     if (e != cudaSuccess) CudaCheck(e, ("step '" + s.name + "' (" + StepKindName(s.kind) + ")").c_str());
 }
 
-void Replica::Enqueue(int n) {
-    if (n <= 0 || n > plan_->max_batch) throw CudaError("batch " + std::to_string(n) + " exceeds the planned maximum");
+void Replica::Enqueue(int n, int off) {
+    if (n <= 0 || off < 0 || off + n > plan_->max_batch) throw CudaError("batch " + std::to_string(off + n) + " exceeds the planned maximum");
     if (!use_graphs_) {
-        for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n);
+        for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n, off);
         return;
     }
-    auto it = graphs_.find(n);
+    const int64_t key = ((int64_t)off << 20) | (int64_t)n;
+    auto it = graphs_.find(key);
     if (it == graphs_.end()) {
         cudaGraph_t graph = nullptr;
         uint64_t before = kernels::LaunchCount();
         CudaCheck(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
         try {
-            for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n);
+            for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n, off);
         } catch (...) {
             cudaStreamEndCapture(stream_, &graph);
             if (graph) cudaGraphDestroy(graph);
@@ -278,13 +297,14 @@ void Replica::Enqueue(int n) {
         CudaCheck(e, "cudaGraphInstantiate");
         if (graphs_.size() >= 64) {  // bound the cache
             cudaGraphExecDestroy(graphs_.begin()->second);
+            graph_launches_.erase(graphs_.begin()->first);
             graphs_.erase(graphs_.begin());
         }
-        it = graphs_.emplace(n, exec).first;
-        graph_launches_[n] = launches_per_forward_;
+        it = graphs_.emplace(key, exec).first;
+        graph_launches_[key] = launches_per_forward_;
     }
     CudaCheck(cudaGraphLaunch(it->second, stream_), "cudaGraphLaunch");
-    kernels::CountLaunch(graph_launches_[n]);
+    kernels::CountLaunch(graph_launches_[key]);
 }
 
 void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
@@ -292,12 +312,38 @@ void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std:
     std::lock_guard<std::mutex> lk(mu_);
     DeviceGuard g(device_);
     const Plan& P = *plan_;
-    for (size_t i = 0; i < P.inputs.size(); ++i) {
-        const TensorDesc& t = P.tensors[P.inputs[i]];
-        size_t bytes = (size_t)n * t.C * t.H * t.W * 4;
-        CudaCheck(cudaMemcpyAsync(BufferPtr(t.buffer), host_inputs[i], bytes, cudaMemcpyHostToDevice, stream_), "H2D input");
+    // Large batches are pipelined in sub-batches: the H2D copy of sub-batch k+1 (copy stream) overlaps the forward
+    // of sub-batch k (compute stream).  The fp32 NCHW input is 602 KB per image, so at bs256 the PCIe transfer is
+    // as long as the whole forward; without overlap the two add up.
+    const int chunk = pipeline_chunk_ > 0 ? pipeline_chunk_ : n;
+    const int pieces = std::min<int>((n + chunk - 1) / chunk, (int)copy_events_.size());
+    if (pieces <= 1) {
+        for (size_t i = 0; i < P.inputs.size(); ++i) {
+            const TensorDesc& t = P.tensors[P.inputs[i]];
+            size_t bytes = (size_t)n * t.C * t.H * t.W * 4;
+            CudaCheck(cudaMemcpyAsync(BufferPtr(t.buffer), host_inputs[i], bytes, cudaMemcpyHostToDevice, stream_), "H2D input");
+        }
+        Enqueue(n);
+    } else {
+        const int per = (n + pieces - 1) / pieces;
+        for (int k = 0; k < pieces; ++k) {
+            const int off = k * per, cnt = std::min(per, n - off);
+            if (cnt <= 0) break;
+            for (size_t i = 0; i < P.inputs.size(); ++i) {
+                const TensorDesc& t = P.tensors[P.inputs[i]];
+                const size_t stride = (size_t)t.C * t.H * t.W * 4;
+                CudaCheck(cudaMemcpyAsync((char*)BufferPtr(t.buffer) + off * stride, (const char*)host_inputs[i] + off * stride,
+                                          cnt * stride, cudaMemcpyHostToDevice, copy_stream_), "H2D input (pipelined)");
+            }
+            CudaCheck(cudaEventRecord(copy_events_[k], copy_stream_), "event record");
+        }
+        for (int k = 0; k < pieces; ++k) {
+            const int off = k * per, cnt = std::min(per, n - off);
+            if (cnt <= 0) break;
+            CudaCheck(cudaStreamWaitEvent(stream_, copy_events_[k], 0), "stream wait event");
+            Enqueue(cnt, off);
+        }
     }
-    Enqueue(n);
     for (size_t i = 0; i < P.outputs.size() && i < host_outputs.size(); ++i) {
         const TensorDesc& t = P.tensors[P.outputs[i]];
         size_t bytes = std::min((size_t)n * t.C * t.H * t.W * 4, out_capacity_bytes[i]);

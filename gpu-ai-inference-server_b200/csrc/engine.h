@@ -55,10 +55,13 @@ private:
         kernels::View in, in2, out;
         const float* scale = nullptr;
         const float* shift = nullptr;
+        size_t in_io_stride = 0, in2_io_stride = 0, out_io_stride = 0;  // bytes per sample when the view is graph I/O
     };
 
-    void Enqueue(int n);            // every step on stream_ (captured into a graph when enabled)
-    void EnqueueStep(size_t i, int n);
+    // Every step on stream_ for samples [off, off+n) of the staged batch (captured into a graph when enabled).
+    // Only graph-input / graph-output buffers are indexed by `off`; all intermediate buffers are reused.
+    void Enqueue(int n, int off = 0);
+    void EnqueueStep(size_t i, int n, int off = 0);
     kernels::View MakeView(int tensor) const;
     void* BufferPtr(int buffer) const;
     void* Upload(const void* host, size_t bytes);
@@ -67,6 +70,9 @@ private:
     std::shared_ptr<const Plan> plan_;
     bool use_graphs_;
     cudaStream_t stream_ = nullptr;
+    cudaStream_t copy_stream_ = nullptr;  // H2D of later sub-batches overlaps the forward of earlier ones
+    std::vector<cudaEvent_t> copy_events_;
+    int pipeline_chunk_ = 128;  // sub-batch size of the H2D/compute pipeline (B200_ENGINE_PIPELINE_CHUNK, 0 = off)
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     char* arena_ = nullptr;
     void* flush_buf_ = nullptr;
@@ -74,8 +80,8 @@ private:
     std::vector<void*> allocations_;
     std::vector<const float*> dconst_;  // fp32 device copy of every Plan::consts entry that is used as a vector
     std::vector<Prepared> prepared_;
-    std::map<int, cudaGraphExec_t> graphs_;
-    std::map<int, int> graph_launches_;  // kernels per captured forward, for the launch counter
+    std::map<int64_t, cudaGraphExec_t> graphs_;  // key: (off << 20) | n
+    std::map<int64_t, int> graph_launches_;  // kernels per captured forward, for the launch counter
     int launches_per_forward_ = 0;
     size_t device_bytes_ = 0;
     std::mutex mu_;

@@ -825,7 +825,9 @@ private:
             // graph inputs stay resident for the whole forward so a staged batch can be re-run (device-resident
             // benchmarking); graph outputs stay until the D2H copy
             if (b.role == BufferDesc::Role::Input) { b.first_step = -1; b.last_step = nsteps; }
-            if (b.role == BufferDesc::Role::Output) b.last_step = nsteps;
+            // ... and are never aliased by scratch: with sub-batch pipelining a later sub-batch's early steps run
+            // after an earlier sub-batch has already produced its slice of the output
+            if (b.role == BufferDesc::Role::Output) { b.first_step = -1; b.last_step = nsteps; }
             if (b.last_step < 0) { b.first_step = -1; b.last_step = nsteps; }  // untouched (pass-through)
             if (b.role == BufferDesc::Role::Input && b.last_step < 0) b.last_step = nsteps;
         }

@@ -206,6 +206,7 @@ def test_batch_properties_and_chunking(pkg, repo_dir, monkeypatch):
     or on how the batch is chunked through the arena (max_batch 4 < n)."""
     monkeypatch.setenv("B200_ENGINE_PRECISION", "fp32")
     monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "4")
+    monkeypatch.setenv("B200_ENGINE_PIPELINE_CHUNK", "3")   # also exercise the H2D/compute sub-batch pipeline
     x = synth.to_model_input(synth.synthetic_images_u8(10, start=3000))
     mgr = pkg.InferenceManager(repo_dir)
     try:
@@ -306,3 +307,32 @@ def test_device_queries_and_vector_add(pkg):
     mem = pkg.get_memory_info(0)
     assert mem.total > 100e9 and mem.free <= mem.total and mem.used == mem.total - mem.free
     assert pkg.kernel_launch_count() >= 0
+
+
+def test_multi_gpu_batch_sharding_matches_single_gpu(pkg, repo_dir, monkeypatch):
+    """Replicated weights, contiguous batch split, no collective: a batch served by G replicas must give the
+    per-image results of one replica (skipped on a 1-GPU box)."""
+    g = pkg.get_device_count()
+    if g < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "bf16")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "16")
+    n = 8 * g + 3
+    x = synth.to_model_input(synth.synthetic_images_u8(n, start=5000))
+    outs = {}
+    for devs in ("0", "all"):
+        monkeypatch.setenv("B200_ENGINE_DEVICES", devs)
+        mgr = pkg.InferenceManager(repo_dir)
+        try:
+            mgr.load_model("densenet_onnx")
+            m = mgr.get_model("densenet_onnx")
+            outs[devs] = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [n, 1000])])[0].data.copy()
+            if devs == "all":
+                assert f"{g} GPU replica(s)" in m.get_metadata().description
+                # small requests rotate over replicas and still agree
+                for i in range(2 * g):
+                    y = m.infer([pkg.TensorData("data_0", x[i:i + 1])], [pkg.OutputConfig("fc6_1", [1, 1000])])[0].data
+                    assert np.array_equal(y, outs["0"][i:i + 1])
+        finally:
+            mgr.shutdown()
+    assert np.array_equal(outs["0"], outs["all"])     # same kernels, same per-image arithmetic: bit-identical
