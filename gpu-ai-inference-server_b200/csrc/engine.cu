@@ -119,9 +119,10 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
         a.bias = vec(s.bias);
         a.post_relu = s.post_relu;
         a.pool2 = s.pool2_fused;
+        a.stem_nchw = s.stem_nchw;
         const std::vector<float>& w = P.consts[s.weight].data;  // [Cout][R][S][Cin]
         const int K = s.R * s.S * s.Cin;
-        pr.use_umma = pr.in.dtype != DType::F32;
+        pr.use_umma = s.stem_nchw || pr.in.dtype != DType::F32;
         if (!pr.use_umma) {
             std::vector<float> kn((size_t)K * s.Cout);
             for (int o = 0; o < s.Cout; ++o)
@@ -133,14 +134,15 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
         if (!kernels::UmmaSupported(a))
             throw CudaError("conv '" + s.name + "' has a shape the tcgen05 path does not support in " +
                             PrecisionName(P.precision) + " mode (Cin=" + std::to_string(s.Cin) + ", Cout=" + std::to_string(s.Cout) + ")");
-        const DType mt = pr.in.dtype;
+        const DType mt = s.stem_nchw ? DType::BF16 : pr.in.dtype;  // the stem always multiplies in bf16
         const int esz = (int)DTypeSize(mt);
         const int kc = kernels::UmmaKChunkElems(mt);
         const int cin_pad = kernels::UmmaPaddedCin(s.Cin, s.R, s.S, mt);
         const bool stem = s.Cin < 16;
-        // stem packing: k = r*32 + s*4 + c (8 pixels x 4 channels per filter row, zero padded)
+        // stem packing: k = r*32 + s*4 + c (8 pixels x 4 channels per filter row, zero padded); the fused NCHW stem
+        // starts its 8-pixel window one pixel further left (16-byte aligned rows), so its taps sit at s+1
         const int K_pad = stem ? ((s.R * 32 + kc - 1) / kc * kc) : s.R * s.S * cin_pad;
-        const int bn = s.Cout <= 32 ? 32 : s.Cout <= 64 ? 64 : 128;
+        const int bn = s.stem_nchw ? 64 : s.Cout <= 32 ? 32 : s.Cout <= 64 ? 64 : 128;
         const int cout_pad = (s.Cout + bn - 1) / bn * bn;
         std::vector<float> scale(s.Cout, 1.f);
         if (mt == DType::FP8) {
@@ -166,7 +168,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
                 for (int ss = 0; ss < s.S; ++ss)
                     for (int c = 0; c < s.Cin; ++c) {
                         float v = w[(((size_t)o * s.R + r) * s.S + ss) * s.Cin + c];
-                        int kk = stem ? r * 32 + ss * 4 + c : (r * s.S + ss) * cin_pad + c;
+                        int kk = stem ? r * 32 + (ss + (s.stem_nchw ? 1 : 0)) * 4 + c : (r * s.S + ss) * cin_pad + c;
                         put(o, kk, v);
                     }
         pr.umma.w = Upload(packed.data(), packed.size());

@@ -34,6 +34,7 @@ struct ConvArgs {
     const float* bias = nullptr;  // [Cout]
     bool post_relu = false;
     bool pool2 = false;  // A rows are 2x2 averages of (prologue-transformed) input pixels
+    bool stem_nchw = false;  // `in` is the caller's fp32 NCHW image batch (7x7/s2/p3 stem, see kernels_stem.cu)
 };
 
 // ---- fp32 SIMT path ("FP32 reference mode"; also every rank-2 GEMM) ----
@@ -53,6 +54,10 @@ cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t strea
 int UmmaKChunkElems(DType mma_dtype);                       // elements per 128-byte K chunk
 int UmmaPaddedCin(int Cin, int R, int S, DType mma_dtype);  // per-tap channel padding used by the A loader
 bool UmmaSupported(const ConvArgs& a);
+// 7x7/s2/p3 image stem straight from fp32 NCHW (kernels_stem.cu); `tensor_map` covers bf16 weights packed
+// [64][256] with k = r*32 + (s+1)*4 + c.
+cudaError_t ConvStemNchw(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
+bool StemNchwSupported(const ConvArgs& a);
 
 // ---- memory-bound kernels (templated on element type inside) ----
 cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);

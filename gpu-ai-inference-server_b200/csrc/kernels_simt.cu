@@ -404,6 +404,74 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_simt_f32_kernel(Co
     }
 }
 
+// ------------------------------------------------------------------ rank-2 GEMM (classifier, MatMul/Gemm graphs)
+// out[m][n] = relu?(bias[n] + sum_k A[m][k] * W[k][n]); A rows are in_pitch apart, W is [K][Cout] row-major.
+// 32 x 64 output tile per CTA (2 x 4 per thread), K in steps of 32 with register prefetch of the next tiles, so a
+// batch-256 x 1000-class classifier spreads over 128 CTAs instead of the 32 the implicit-GEMM tiling would give.
+__global__ void __launch_bounds__(256) fc_f32_kernel(ConvP p) {
+    constexpr int BM = 32, BN = 64, BK = 32;
+    __shared__ float As[BK][BM + 1];
+    __shared__ float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads: rows ty*2.., cols tx*4..
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // A loader: thread -> (row = tid / 8, k quad = tid % 8); B loader: two (k row, n quad) pieces per thread
+    const int a_row = tid >> 3, a_k = (tid & 7) * 4;
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+    float acc[2][4] = {};
+    float ra[4], rb[2][4];
+    auto fetch = [&](int k0) {
+        const int m = m0 + a_row;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + a_k + q;
+            ra[q] = (m < p.M && k < p.K) ? p.in[(size_t)m * p.in_pitch + p.in_coff + k] : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + b_k + 16 * h;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int n = n0 + b_n + q;
+                rb[h][q] = (k < p.K && n < p.Cout) ? p.w[(size_t)k * p.Cout + n] : 0.f;
+            }
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) As[a_k + q][a_row] = ra[q];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            *reinterpret_cast<float4*>(&Bs[b_k + 16 * h][b_n]) = make_float4(rb[h][0], rb[h][1], rb[h][2], rb[h][3]);
+        __syncthreads();
+        if (k0 + BK < p.K) fetch(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+            acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+            acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+            acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.Cout) continue;
+            float v = acc[i][j] + (p.bias ? p.bias[n] : 0.f);
+            if (p.post_relu) v = fmaxf(v, 0.f);
+            p.out[(size_t)m * p.out_pitch + p.out_coff + n] = v;
+        }
+    }
+}
+
 }  // namespace
 
 // ====================================================================== launchers
@@ -421,7 +489,10 @@ cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t strea
     p.vecB = (a.Cout % 4 == 0 && ((uintptr_t)w_kn % 16) == 0);
     p.vecC = (a.out.pitch % 4 == 0 && a.out.c_off % 4 == 0 && ((uintptr_t)p.out % 16) == 0);
     if (p.M <= 0) return cudaSuccess;
-    if (a.Cout <= 32) {
+    if (a.R == 1 && a.S == 1 && a.in.H == 1 && a.in.W == 1 && p.Ho == 1 && p.Wo == 1 && !a.pre_scale) {
+        dim3 grid((p.M + 31) / 32, (a.Cout + 63) / 64);
+        fc_f32_kernel<<<grid, 256, 0, stream>>>(p);
+    } else if (a.Cout <= 32) {
         constexpr int BM = 128, BN = 32;
         dim3 grid((p.M + BM - 1) / BM, (a.Cout + BN - 1) / BN);
         conv_simt_f32_kernel<BM, BN, 16, 4, 4><<<grid, 256, 0, stream>>>(p);

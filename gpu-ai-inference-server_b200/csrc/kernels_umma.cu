@@ -27,278 +27,12 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "umma_ptx.cuh"
 
 namespace b200 {
 namespace kernels {
 
 namespace {
-
-constexpr int kThreads = 448;
-constexpr int kTileM = 128;
-constexpr int kRowBytes = 128;             // one K chunk of one row: 128 bytes (the swizzle span)
-constexpr int kATileBytes = kTileM * kRowBytes;
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t SmemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void MbarInit(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void MbarArrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(bar)) : "memory");
-}
-__device__ __forceinline__ void MbarArriveExpectTx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(SmemAddr(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Non-blocking probe (mbarrier.test_wait never suspends the thread).
-__device__ __forceinline__ bool MbarTest(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(SmemAddr(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// A lost arrive must become an error, not a hung GPU: trap after a generous spin budget.
-__device__ __noinline__ void MbarTimeout() {
-    printf("conv_umma: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-    __trap();
-}
-__device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
-    if (MbarTryWait(bar, parity)) return;
-    uint32_t spins = 0;
-    while (!MbarTryWait(bar, parity)) {
-        if (++spins > (1u << 24)) MbarTimeout();
-    }
-}
-// One lane of a fully converged warp; the compiler keeps the surrounding code on the uniform datapath
-// (descriptors in uniform registers) instead of wrapping every tcgen05/TMA instruction in a waterfall loop.
-__device__ __forceinline__ bool ElectOne() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "elect.sync _|P1, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P1;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void FenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void TcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void TmaLoad2D(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void PrefetchTensorMap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
-}
-
-__device__ __forceinline__ void TmemAlloc(uint32_t* slot, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(slot)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void TmemDealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T ; KIND 0: kind::f16 (bf16 operands), 1: kind::f8f6f4 (e4m3 operands)
-template <int KIND>
-__device__ __forceinline__ void UmmaSS(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    if (KIND == 0) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-            : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-// Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed.
-__device__ __forceinline__ void UmmaCommit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemAddr(bar)) : "memory");
-}
-
-__device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void TmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
-// 8-row groups | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t MakeSmemDesc(uint32_t smem_byte_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6) | a_format [7,10) |
-// b_format [10,13) | a/b K-major (0) | N>>3 [17,23) | M>>4 [24,29).
-__host__ __device__ constexpr uint32_t MakeInstrDesc(int fmt, int n) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-
-__device__ __forceinline__ uint4 LdgNc(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint2 LdgNc8(const void* p) {
-    uint2 r;
-    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void StsV4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// ------------------------------------------------------------------ element traits
-template <typename T> struct MmaElem;
-template <> struct MmaElem<__nv_bfloat16> {
-    static constexpr int kKind = 0, kFmt = 1;  // kind::f16, BF16
-    static constexpr int kPerVec = 8;          // elements per 16 bytes
-    static constexpr int kChunk = 64;          // elements per 128-byte K chunk
-    static constexpr int kStepK = 16;          // elements per tcgen05.mma (32 bytes)
-    __device__ static void Unpack(const uint4& v, float* f) {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            f[2 * i] = __uint_as_float(w[i] << 16);
-            f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-        }
-    }
-    __device__ static uint4 Pack(const float* f) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        return make_uint4(w[0], w[1], w[2], w[3]);
-    }
-};
-template <> struct MmaElem<__nv_fp8_e4m3> {
-    static constexpr int kKind = 1, kFmt = 0;  // kind::f8f6f4, E4M3
-    static constexpr int kPerVec = 16;
-    static constexpr int kChunk = 128;
-    static constexpr int kStepK = 32;
-    __device__ static void Unpack(const uint4& v, float* f) {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                __half2_raw hr = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * h)) & 0xFFFFu), __NV_E4M3);
-                float2 t = __half22float2(*reinterpret_cast<__half2*>(&hr));
-                f[4 * i + 2 * h] = t.x;
-                f[4 * i + 2 * h + 1] = t.y;
-            }
-        }
-    }
-    __device__ static uint4 Pack(const float* f) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i], f[4 * i + 1]), __NV_SATFINITE, __NV_E4M3);
-            uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(f[4 * i + 2], f[4 * i + 3]), __NV_SATFINITE, __NV_E4M3);
-            w[i] = lo | (hi << 16);
-        }
-        return make_uint4(w[0], w[1], w[2], w[3]);
-    }
-};
-
-// ------------------------------------------------------------------ packed prologue math
-// Folded BatchNorm (+ReLU) on packed pairs: one fma.rn[.relu] per two channels.
-template <bool RELU> __device__ __forceinline__ uint32_t FmaBf16x2(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    if (RELU) asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    else asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-template <bool RELU> __device__ __forceinline__ uint32_t FmaF16x2(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    if (RELU) asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    else asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t E4m3x2ToF16x2(uint32_t v16) {
-    uint32_t d;
-    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(d) : "h"((unsigned short)v16));
-    return d;
-}
-__device__ __forceinline__ uint32_t F16x2ToE4m3x2(uint32_t v) {
-    unsigned short d;
-    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(d) : "r"(v));
-    return (uint32_t)d;
-}
-// Packs two fp32 per-channel constants for the packed prologue of each MMA element type.
-template <typename T> __device__ __forceinline__ uint32_t PackPair(float a, float b);
-template <> __device__ __forceinline__ uint32_t PackPair<__nv_bfloat16>(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-template <> __device__ __forceinline__ uint32_t PackPair<__nv_fp8_e4m3>(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-// y = [relu](x * scale + shift) on one 16-byte piece; sc/sh hold one packed pair per two channels.
-template <typename T, bool RELU> __device__ __forceinline__ uint4 ProloguePiece(uint4 v, const uint32_t* sc, const uint32_t* sh);
-template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_bfloat16, true>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
-    return make_uint4(FmaBf16x2<true>(v.x, sc[0], sh[0]), FmaBf16x2<true>(v.y, sc[1], sh[1]),
-                      FmaBf16x2<true>(v.z, sc[2], sh[2]), FmaBf16x2<true>(v.w, sc[3], sh[3]));
-}
-template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_bfloat16, false>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
-    return make_uint4(FmaBf16x2<false>(v.x, sc[0], sh[0]), FmaBf16x2<false>(v.y, sc[1], sh[1]),
-                      FmaBf16x2<false>(v.z, sc[2], sh[2]), FmaBf16x2<false>(v.w, sc[3], sh[3]));
-}
-template <bool RELU> __device__ __forceinline__ uint32_t PrologueWordFp8(uint32_t w, const uint32_t* sc, const uint32_t* sh) {
-    uint32_t lo = FmaF16x2<RELU>(E4m3x2ToF16x2(w & 0xFFFFu), sc[0], sh[0]);
-    uint32_t hi = FmaF16x2<RELU>(E4m3x2ToF16x2(w >> 16), sc[1], sh[1]);
-    return F16x2ToE4m3x2(lo) | (F16x2ToE4m3x2(hi) << 16);
-}
-template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_fp8_e4m3, true>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
-    return make_uint4(PrologueWordFp8<true>(v.x, sc, sh), PrologueWordFp8<true>(v.y, sc + 2, sh + 2),
-                      PrologueWordFp8<true>(v.z, sc + 4, sh + 4), PrologueWordFp8<true>(v.w, sc + 6, sh + 6));
-}
-template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_fp8_e4m3, false>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
-    return make_uint4(PrologueWordFp8<false>(v.x, sc, sh), PrologueWordFp8<false>(v.y, sc + 2, sh + 2),
-                      PrologueWordFp8<false>(v.z, sc + 4, sh + 4), PrologueWordFp8<false>(v.w, sc + 6, sh + 6));
-}
 
 struct UParams {
     const void* in;
@@ -336,15 +70,6 @@ template <int BN> struct TileCfg {
     static constexpr int kTmemCols = BN == 128 ? 256 : BN == 64 ? 128 : 64;
     static constexpr int kSmemBytes = kStages * kStageBytes + kVecSmemBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
-
-__device__ __forceinline__ void CpAsync16(uint32_t dst, const void* src, bool valid) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
-}
-__device__ __forceinline__ void CpAsync8(uint32_t dst, const void* src, bool valid) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(valid ? 8 : 0) : "memory");
-}
-__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void CpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Walks the (tile, K-chunk) sequence of this CTA, visiting every second chunk (one producer group's share).
 struct ChunkIter {
@@ -840,15 +565,6 @@ struct HParams {
     int chunks_per_tap;  // weight chunks (128 B of K) per tap
 };
 
-__device__ __forceinline__ uint64_t MakeSmemDescNoSwizzle(uint32_t smem_byte_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_byte_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;  // layout_type 0 = SWIZZLE_NONE
-}
-
 template <typename MmaT, typename OutT>
 __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HParams p) {
     using ME = MmaElem<MmaT>;
@@ -1138,6 +854,7 @@ int UmmaPaddedCin(int Cin, int, int, DType d) {
 }
 
 bool UmmaSupported(const ConvArgs& a) {
+    if (a.stem_nchw) return StemNchwSupported(a);
     const DType it = a.in.dtype, ot = a.out.dtype;
     if (it != DType::BF16 && it != DType::FP8) return false;
     if (ot != DType::BF16 && ot != DType::FP8) return false;
@@ -1158,6 +875,7 @@ bool UmmaSupported(const ConvArgs& a) {
 
 cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream) {
     if (!UmmaSupported(a) || !w.tensor_map) return cudaErrorInvalidValue;
+    if (a.stem_nchw) return ConvStemNchw(a, w, stream);
     const DType it = a.in.dtype, ot = a.out.dtype;
     const bool stem = a.Cin < 16;
     const int kc = UmmaKChunkElems(it);

@@ -96,6 +96,7 @@ public:
         LowerInputs();
         for (size_t i = 0; i < g_.nodes.size(); ++i) LowerNode((int)i);
         LowerOutputs();
+        FuseStemInput();
         Liveness();
         Account();
         return std::move(plan_);
@@ -805,6 +806,34 @@ private:
         }
     }
 
+    // The bf16 NHWC4 copy of an image input exists only to feed the stem conv; when that conv is the 7x7/s2 stem
+    // the tcgen05 stem kernel converts fp32 NCHW rows on the fly, so the layout pass and its buffer disappear.
+    void FuseStemInput() {
+        if (plan_.precision == Precision::FP32) return;
+        for (size_t k = 0; k < plan_.steps.size(); ++k) {
+            if (plan_.steps[k].kind != StepKind::NchwToNhwc) continue;
+            const int raw = plan_.steps[k].in, nhwc = plan_.steps[k].out;
+            int users = 0, conv = -1;
+            for (size_t j = 0; j < plan_.steps.size(); ++j) {
+                if (j == k) continue;
+                const Step& s = plan_.steps[j];
+                if (s.in == nhwc || s.in2 == nhwc) { ++users; conv = (int)j; }
+            }
+            bool is_output = false;
+            for (int o : plan_.outputs) is_output |= (o == nhwc);
+            if (users != 1 || is_output) continue;
+            Step& c = plan_.steps[conv];
+            const TensorDesc& t = plan_.tensors[nhwc];
+            if (c.kind != StepKind::Conv || c.in != nhwc || c.pre_scale >= 0 || c.pool2_fused) continue;
+            if (!StemFusable(c.Cin, c.Cout, c.R, c.S, c.stride, c.pad, t.H, t.W)) continue;
+            c.in = raw;
+            c.stem_nchw = true;
+            plan_.buffers[t.buffer].elems_per_sample = 0;  // never materialised
+            plan_.steps.erase(plan_.steps.begin() + k);
+            --k;
+        }
+    }
+
     // ------------------------------------------------------------------ arena
     void Liveness() {
         const int nsteps = (int)plan_.steps.size();
@@ -905,6 +934,11 @@ void JsonEscape(std::ostringstream& os, const std::string& s) {
 
 }  // namespace
 
+bool StemFusable(int Cin, int Cout, int R, int S, int stride, int pad, int H, int W) {
+    return Cin >= 1 && Cin <= 3 && R == 7 && S == 7 && stride == 2 && pad == 3 && Cout >= 16 && Cout <= 64 && Cout % 16 == 0 &&
+           W % 4 == 0 && W >= 8 && W <= 1024 && H >= 2;
+}
+
 Plan BuildPlan(const onnx::Model& model, Precision precision, int max_batch) {
     return Lowerer(model, precision, max_batch).Run();
 }
@@ -953,7 +987,8 @@ std::string Plan::ToJson() const {
             os << ",\"R\":" << s.R << ",\"S\":" << s.S << ",\"stride\":" << s.stride << ",\"pad\":" << s.pad
                << ",\"Cin\":" << s.Cin << ",\"Cout\":" << s.Cout << ",\"pre_bn\":" << (s.pre_scale >= 0 ? "true" : "false")
                << ",\"pre_relu\":" << (s.pre_relu ? "true" : "false") << ",\"bias\":" << (s.bias >= 0 ? "true" : "false")
-               << ",\"post_relu\":" << (s.post_relu ? "true" : "false") << ",\"pool2_fused\":" << (s.pool2_fused ? "true" : "false");
+               << ",\"post_relu\":" << (s.post_relu ? "true" : "false") << ",\"pool2_fused\":" << (s.pool2_fused ? "true" : "false")
+               << ",\"stem_nchw\":" << (s.stem_nchw ? "true" : "false");
         if (s.kind == StepKind::MaxPool || s.kind == StepKind::AvgPool)
             os << ",\"k\":" << s.R << ",\"stride\":" << s.stride << ",\"pad\":" << s.pad;
         if (s.kind == StepKind::BnRelu || s.kind == StepKind::GlobalAvgPool)

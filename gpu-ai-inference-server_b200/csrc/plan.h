@@ -76,6 +76,7 @@ struct Step {
     bool pre_relu = false;
     bool post_relu = false;
     bool pool2_fused = false;  // 2x2/s2 AveragePool commuted in front of a 1x1 conv (linear ops commute)
+    bool stem_nchw = false;    // 7x7/s2/p3 image stem reading the caller's fp32 NCHW input directly (layout pass fused)
     bool count_include_pad = false;
     bool ceil_mode = false;
     // BnRelu / GlobalAvgPool prologue
@@ -112,6 +113,10 @@ struct Plan {
 
     std::string ToJson() const;
 };
+
+// True when a convolution is the image stem the fused tcgen05 stem kernel executes straight from fp32 NCHW
+// (7x7, stride 2, pad 3, <= 4 input channels, <= 64 output channels).
+bool StemFusable(int Cin, int Cout, int R, int S, int stride, int pad, int H, int W);
 
 // Throws std::runtime_error with a descriptive message for unsupported graphs.
 Plan BuildPlan(const onnx::Model& model, Precision precision, int max_batch);
