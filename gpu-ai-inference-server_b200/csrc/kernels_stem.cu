@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
     __syncthreads();
     TcFenceAfter();
     const uint32_t tmem_base = *tmem_slot;
+    GridDepLaunch();
+    if (warp < 12) GridDepWait();
 
     if (warp < 8) {
         // =========================================================== input producers: fp32 NCHW -> bf16 (c0,c1,c2,0) pixels
@@ -284,9 +286,9 @@ cudaError_t LaunchStem(const CUtensorMap& tm, const SParams& p, cudaStream_t str
     }
     const int smem = 1024 + kStemWBytes + 2 * p.buf_bytes + 2 * kStemN * 4 + 256;
     const int grid = p.num_strips < sm_count[dev] ? p.num_strips : sm_count[dev];
-    kern<<<grid, kThreads, smem, stream>>>(tm, p);
+    cudaError_t le = LaunchPdl(kern, grid, kThreads, smem, stream, tm, p);
     CountLaunch();
-    return cudaGetLastError();
+    return le;
 }
 
 }  // namespace

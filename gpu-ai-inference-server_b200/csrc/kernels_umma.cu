@@ -189,6 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     __syncthreads();
     TcFenceAfter();
     const uint32_t tmem_base = *tmem_slot;
+    GridDepLaunch();
+    if (warp < 12) GridDepWait();  // activations: readers (producers) and writers (epilogue); weight TMA runs ahead
 
     if (warp < 8) {
         // =========================================================== A producers
@@ -614,6 +616,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_halo_kernel(const __grid_
     __syncthreads();
     TcFenceAfter();
     const uint32_t tmem_base = *tmem_slot;
+    GridDepLaunch();
+    if (warp < 12) GridDepWait();
 
     if (warp < 8) {
         // =========================================================== patch producers (256 threads, cp.async)
@@ -797,9 +801,9 @@ cudaError_t LaunchHalo(const CUtensorMap& tm, const HParams& p, cudaStream_t str
         sm_count[dev] = n > 0 ? n : 148;
     }
     int grid = p.num_tiles < sm_count[dev] ? p.num_tiles : sm_count[dev];
-    kern<<<grid, kThreads, kHaloSmemBytes, stream>>>(tm, p);
+    cudaError_t le = LaunchPdl(kern, grid, kThreads, kHaloSmemBytes, stream, tm, p);
     CountLaunch();
-    return cudaGetLastError();
+    return le;
 }
 
 template <typename MmaT, typename OutT, int BN, int MODE>
@@ -819,9 +823,9 @@ cudaError_t Launch(const CUtensorMap& tm, const UParams& p, cudaStream_t stream)
     }
     int tiles = p.num_m_tiles * p.num_n_tiles;
     int grid = tiles < sm_count[dev] ? tiles : sm_count[dev];
-    kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tm, p);
+    cudaError_t le = LaunchPdl(kern, grid, kThreads, Cfg::kSmemBytes, stream, tm, p);
     CountLaunch();
-    return cudaGetLastError();
+    return le;
 }
 
 template <typename MmaT, typename OutT, int MODE>

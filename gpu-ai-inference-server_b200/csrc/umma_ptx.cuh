@@ -6,8 +6,11 @@
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 
+#include <cuda_runtime.h>
+
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 
 namespace b200 {
 namespace kernels {
@@ -76,6 +79,28 @@ __device__ __forceinline__ bool ElectOne() {
         : "=r"(pred));
     return pred != 0;
 }
+// Programmatic dependent launch: `GridDepLaunch` lets the next kernel of the stream start its preamble (barrier
+// init, TMEM allocation, weight TMA) while this grid is still running; `GridDepWait` blocks until the previous grid
+// has completed and its memory is visible - every thread that touches activations calls it first.
+__device__ __forceinline__ void GridDepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void GridDepLaunch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Launch with the programmatic-stream-serialization attribute (the kernel must call GridDepWait()).
+template <typename... KArgs, typename... Args>
+inline cudaError_t LaunchPdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 __device__ __forceinline__ void FenceBarrierInit() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
