@@ -37,6 +37,12 @@ struct ConvArgs {
     bool stem_nchw = false;  // `in` is the caller's fp32 NCHW image batch (7x7/s2/p3 stem, see kernels_stem.cu)
 };
 
+// A CUtensorMap by value (128 bytes, 64-byte aligned) without pulling <cuda.h> into every translation unit.
+struct alignas(64) TensorMap { unsigned char bytes[128]; };
+// Tiled TMA descriptor: dims/box innermost first, strides_bytes for dims 1..rank-1.  Returns 0 on success.
+int MakeTensorMap(TensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128);
+
 // ---- fp32 SIMT path ("FP32 reference mode"; also every rank-2 GEMM) ----
 // w_kn: fp32 [K = R*S*Cin][Cout]
 cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t stream);
@@ -58,6 +64,10 @@ bool UmmaSupported(const ConvArgs& a);
 // [64][256] with k = r*32 + (s+1)*4 + c.
 cudaError_t ConvStemNchw(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
 bool StemNchwSupported(const ConvArgs& a);
+
+// 3x3/s1/p1 conv of a 128-byte-per-pixel bottleneck into <= 32 channels, patches loaded by 4-D TMA (kernels_conv3x3.cu)
+bool Conv3x3TmaSupported(const ConvArgs& a);
+cudaError_t Conv3x3Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
 
 // ---- memory-bound kernels (templated on element type inside) ----
 cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);

@@ -1,0 +1,268 @@
+// kernels_conv3x3.cu — 3x3 / stride 1 / pad 1 convolution of a 128-byte-per-pixel bottleneck (Cin = 128 e4m3 or
+// 64..128 bf16 channels) into <= 32 output channels: the second conv of every DenseNet dense layer.
+//
+// Replaces the Conv node ONNX Runtime would execute inside `Ort::Session::Run` (reference
+// inference_engine/src/model.cpp:1264-1270) for `/features/denseblockX/denselayerY/conv2/Conv`.
+//
+// A CTA owns TH x TW output pixels of one image.  ONE 4-D TMA box {128 B of channels, 16 pixels, TH+2 rows, 1 image}
+// lands the zero-padded input patch (out-of-image coordinates are zero-filled by the TMA unit = the conv padding) as
+// [slot = row*16 + x][128 B] in SWIZZLE_128B layout, which is exactly the K-major UMMA operand layout with one
+// pixel per row.  The nine filter taps are nine ROW-SHIFTED views of that tile: output slot m reads patch slot
+// m + fr*16 + fs, i.e. the same descriptor with its start address advanced by (fr*16 + fs) * 128 bytes.  (Measured
+// on B200: the tensor core applies the 128-byte XOR swizzle to ABSOLUTE shared-memory address bits, exactly like
+// the TMA unit that wrote the tile, so a start address that is not a multiple of 8 rows needs no fix-up; the
+// descriptor's matrix-base-offset field must stay 0 - setting it to the row phase gives wrong results.)
+// No thread ever touches the activations: the producer
+// is one elected lane issuing TMA, so the whole CTA is 6 warps (TMA, MMA, 4 epilogue).  The 9 weight tiles
+// ([32][128 B] each) are TMA-loaded once and stay resident; patches stream through a ring of kBufs buffers.
+#include <cstdlib>
+
+#include "kernels.h"
+#include "umma_ptx.cuh"
+
+namespace b200 {
+namespace kernels {
+
+namespace {
+
+constexpr int kC3Threads = 192;
+constexpr int kC3PW = 16;                          // patch width in slots (TW <= 14)
+constexpr int kC3PlaneBytes = 10 * kC3PW * 128;    // (TH+2 <= 10) rows x 16 slots x 128 B = 20 KB per 128-byte K plane
+constexpr int kC3BN = 32;
+constexpr int kC3Acc = 4;                          // TMEM accumulators of 32 columns
+
+template <int CPT> struct C3Cfg {                  // CPT = 128-byte K planes per pixel (1: e4m3, 2: bf16)
+    static constexpr int kBufs = CPT == 1 ? 6 : 3;
+    static constexpr int kWeightBytes = 9 * CPT * kC3BN * 128;
+    static constexpr int kBufBytes = CPT * kC3PlaneBytes;
+    static constexpr int kSmemBytes = 1024 + kWeightBytes + kBufs * kBufBytes + 1024 /*junk-row overreach*/ + 256;
+};
+
+struct C3Params {
+    void* out;
+    const float* out_scale;
+    const float* bias;
+    int post_relu;
+    int H, W, out_pitch, out_coff, Cout, in_coff;
+    int n, TH, TW, tiles_x, tiles_y, num_tiles;
+    int ksteps;  // K steps (32 B) per 128-byte plane that carry data (4 when the plane is full)
+};
+
+template <typename MmaT, typename OutT>
+__global__ void __launch_bounds__(kC3Threads, 1)
+conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in, const C3Params p) {
+    using ME = MmaElem<MmaT>;
+    constexpr int CPT = sizeof(MmaT) == 1 ? 1 : 2;
+    using Cfg = C3Cfg<CPT>;
+    constexpr int NB = Cfg::kBufs;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;
+    uint8_t* s_patch = smem + Cfg::kWeightBytes;
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_patch + NB * Cfg::kBufBytes + 1024);
+    uint64_t* patch_full = w_bar + 1;
+    uint64_t* patch_empty = patch_full + NB;
+    uint64_t* tmem_full = patch_empty + NB;
+    uint64_t* tmem_empty = tmem_full + kC3Acc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kC3Acc);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        MbarInit(w_bar, 1);
+        for (int b = 0; b < NB; ++b) {
+            MbarInit(&patch_full[b], 1);
+            MbarInit(&patch_empty[b], 1);
+        }
+        for (int a = 0; a < kC3Acc; ++a) {
+            MbarInit(&tmem_full[a], 1);
+            MbarInit(&tmem_empty[a], 128);
+        }
+        FenceBarrierInit();
+        PrefetchTensorMap(&tmap_w);
+        PrefetchTensorMap(&tmap_in);
+    }
+    if (warp == 1) TmemAlloc(tmem_slot, kC3Acc * kC3BN);
+    TcFenceBefore();
+    __syncthreads();
+    TcFenceAfter();
+    const uint32_t tmem_base = *tmem_slot;
+    GridDepLaunch();
+
+    if (warp == 0) {
+        // =========================================================== TMA producer: weights once, then the patch ring
+        if (ElectOne()) {
+            MbarArriveExpectTx(w_bar, (uint32_t)Cfg::kWeightBytes);
+            for (int t = 0; t < 9 * CPT; ++t) TmaLoad2D(s_w + t * kC3BN * 128, &tmap_w, w_bar, t * ME::kChunk, 0);
+        }
+        __syncwarp();
+        GridDepWait();  // the patches are the previous kernel's output
+        const uint32_t box_bytes = (uint32_t)(CPT * (p.TH + 2) * kC3PW * 128);
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
+            const uint32_t buf = k % NB, par = ((k / NB) & 1u) ^ 1u;
+            MbarWait(&patch_empty[buf], par);
+            if (ElectOne()) {
+                const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+                MbarArriveExpectTx(&patch_full[buf], box_bytes);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)
+                    TmaLoad4D(s_patch + buf * Cfg::kBufBytes + j * kC3PlaneBytes, &tmap_in, &patch_full[buf], p.in_coff + j * ME::kChunk,
+                              tx * p.TW - 1, ty * p.TH - 1, img);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer
+        constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, kC3BN);
+        const uint64_t b_base = MakeSmemDesc(SmemAddr(s_w));
+        const uint32_t patch_addr = SmemAddr(s_patch);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        MbarWait(w_bar, 0);
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
+            const uint32_t buf = k % NB, ph = (k / NB) & 1u;
+            const uint32_t acc = k % kC3Acc, acc_ph = (k / kC3Acc) & 1u;
+            MbarWait(&tmem_empty[acc], acc_ph ^ 1u);
+            MbarWait(&patch_full[buf], ph);
+            TcFenceAfter();
+            if (ElectOne()) {
+                const uint32_t d_addr = tmem_u + acc * kC3BN;
+                const uint32_t a_buf = patch_addr + buf * Cfg::kBufBytes;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) {
+                        // rows shifted by (fr*16 + fs) slots of 128 B
+                        const uint64_t a_desc = MakeSmemDesc(a_buf + j * kC3PlaneBytes + ((tap / 3) * kC3PW + (tap % 3)) * 128);
+                        const uint64_t b_desc = b_base + (uint64_t)((tap * CPT + j) * (kC3BN * 128 / 16));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            if (ks < p.ksteps) UmmaSS<ME::kKind>(d_addr, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (tap | j | ks) ? 1u : 0u);
+                    }
+                }
+                UmmaCommit(&patch_empty[buf]);
+                UmmaCommit(&tmem_full[acc]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================================================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1)
+        const int e = warp & 3;
+        OutT* out = reinterpret_cast<OutT*>(p.out);
+        float sc[32], bi[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            sc[q] = q < p.Cout ? p.out_scale[q] : 0.f;
+            bi[q] = (p.bias && q < p.Cout) ? p.bias[q] : 0.f;
+        }
+        const int mrow = e * 32 + lane;
+        const int y = mrow / kC3PW, x = mrow - y * kC3PW;
+        GridDepWait();  // stores may alias buffers the previous kernel still reads
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
+            const uint32_t acc = k % kC3Acc, acc_phase = (k / kC3Acc) & 1u;
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+            MbarWait(&tmem_full[acc], acc_phase);
+            TcFenceAfter();
+            uint32_t r[32];
+            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kC3BN, r);
+            TmemLoadWait();
+            TcFenceBefore();
+            MbarArrive(&tmem_empty[acc]);  // the accumulator is in registers: release it before the stores
+            const int oy = ty * p.TH + y, ox = tx * p.TW + x;
+            if (y < p.TH && x < p.TW && oy < p.H && ox < p.W) {
+                constexpr int kWords = 32 * (int)sizeof(OutT) / 4;
+                uint32_t w[kWords];
+                if (p.post_relu) EpiloguePack32<OutT, true>(r, sc, bi, w);
+                else EpiloguePack32<OutT, false>(r, sc, bi, w);
+                OutT* orow = out + ((size_t)(img * p.H + oy) * p.W + ox) * p.out_pitch + p.out_coff;
+                constexpr int kPer = 16 / (int)sizeof(OutT);  // channels per 16-byte store
+#pragma unroll
+                for (int q = 0; q < kWords / 4; ++q)
+                    if (q * kPer < p.Cout) *reinterpret_cast<uint4*>(orow + q * kPer) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+            __syncwarp();
+        }
+    }
+    TcFenceBefore();
+    __syncthreads();
+    if (warp == 1) {
+        TcFenceAfter();
+        TmemDealloc(tmem_base, kC3Acc * kC3BN);
+    }
+}
+
+template <typename MmaT, typename OutT>
+cudaError_t LaunchC3(const CUtensorMap& tw, const CUtensorMap& tin, const C3Params& p, cudaStream_t stream) {
+    using Cfg = C3Cfg<sizeof(MmaT) == 1 ? 1 : 2>;
+    auto kern = conv3x3_tma_kernel<MmaT, OutT>;
+    static int sm_count[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!sm_count[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count[dev] = n > 0 ? n : 148;
+    }
+    const int grid = p.num_tiles < sm_count[dev] ? p.num_tiles : sm_count[dev];
+    cudaError_t le = LaunchPdl(kern, grid, kC3Threads, Cfg::kSmemBytes, stream, tw, tin, p);
+    CountLaunch();
+    return le;
+}
+
+}  // namespace
+
+bool Conv3x3TmaSupported(const ConvArgs& a) {
+    const DType it = a.in.dtype, ot = a.out.dtype;
+    if (it != ot || (it != DType::BF16 && it != DType::FP8)) return false;
+    if (!(a.R == 3 && a.S == 3 && a.stride == 1 && a.pad == 1) || a.pre_scale || a.pool2 || a.stem_nchw) return false;
+    const int esz = (int)DTypeSize(it);
+    const int step_k = 32 / esz;
+    if (a.Cout > 32 || a.Cout % (16 / esz) != 0) return false;
+    // the patch box is 128 bytes of channels per K plane: e4m3 takes Cin <= 128 (one plane, partial K steps allowed),
+    // bf16 exactly Cin == 128 (two planes)
+    if (a.Cin % step_k != 0 || a.Cin > 128) return false;
+    if (esz == 2 && a.Cin != 128) return false;
+    if ((a.in.pitch * esz) % 16 != 0 || (a.in.c_off * esz) % 16 != 0 || (a.out.pitch * esz) % 16 != 0 || (a.out.c_off * esz) % 16 != 0) return false;
+    if (reinterpret_cast<uintptr_t>(a.in.base) % 16 != 0) return false;
+    // the box always reads 128 bytes of channels: it must stay inside the pixel
+    const int box_ch = 128 / esz;
+    const int planes = a.Cin * esz > 128 ? 2 : 1;
+    if (a.in.c_off + planes * box_ch > a.in.pitch) return false;
+    return a.in.H >= 1 && a.in.W >= 1 && a.in.H == a.out.H && a.in.W == a.out.W;
+}
+
+cudaError_t Conv3x3Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream) {
+    if (!Conv3x3TmaSupported(a) || !w.tensor_map) return cudaErrorInvalidValue;
+    if (a.n <= 0) return cudaSuccess;
+    const DType it = a.in.dtype;
+    const int esz = (int)DTypeSize(it);
+    C3Params p;
+    p.out = a.out.base; p.out_scale = w.out_scale; p.bias = a.bias; p.post_relu = a.post_relu;
+    p.H = a.in.H; p.W = a.in.W; p.out_pitch = a.out.pitch; p.out_coff = a.out.c_off; p.Cout = a.Cout; p.in_coff = a.in.c_off;
+    p.n = a.n;
+    p.TW = p.W % 14 == 0 ? 14 : (p.W < 14 ? p.W : (p.W % 13 == 0 ? 13 : (p.W % 12 == 0 ? 12 : 14)));
+    p.TH = p.H % 8 == 0 ? 8 : (p.H % 7 == 0 ? 7 : (p.H < 8 ? p.H : 8));
+    p.tiles_x = (p.W + p.TW - 1) / p.TW;
+    p.tiles_y = (p.H + p.TH - 1) / p.TH;
+    p.num_tiles = a.n * p.tiles_x * p.tiles_y;
+    const int plane_elems = 128 / esz;
+    const int last = a.Cin % plane_elems;
+    p.ksteps = last == 0 ? 4 : last * esz / 32;
+    TensorMap tin;
+    const uint64_t dims[4] = {(uint64_t)a.in.pitch, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)a.n};
+    const uint64_t strides[3] = {(uint64_t)a.in.pitch * esz, (uint64_t)p.W * a.in.pitch * esz, (uint64_t)p.H * p.W * a.in.pitch * esz};
+    const uint32_t box[4] = {(uint32_t)plane_elems, (uint32_t)kC3PW, (uint32_t)(p.TH + 2), 1u};
+    if (MakeTensorMap(&tin, a.in.base, esz, 4, dims, strides, box, true) != 0) return cudaErrorInvalidValue;
+    const CUtensorMap& tw = *reinterpret_cast<const CUtensorMap*>(w.tensor_map);
+    const CUtensorMap& ti = *reinterpret_cast<const CUtensorMap*>(&tin);
+    if (it == DType::BF16) return LaunchC3<__nv_bfloat16, __nv_bfloat16>(tw, ti, p, stream);
+    return LaunchC3<__nv_fp8_e4m3, __nv_fp8_e4m3>(tw, ti, p, stream);
+}
+
+}  // namespace kernels
+}  // namespace b200

@@ -112,6 +112,64 @@ __device__ __forceinline__ void TmaLoad2D(void* smem_dst, const CUtensorMap* map
         ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void TmaLoad4D(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// TMA store of a shared-memory box (bulk async-group completion).
+__device__ __forceinline__ void TmaStore2D(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((uint64_t)map), "r"(SmemAddr(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void BulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void BulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void BulkWait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void NamedBarSync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// ---- packed epilogue math: two fp32 lanes per instruction, ReLU folded into the narrowing convert
+__device__ __forceinline__ float2 Fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+// (lo, hi) -> two e4m3 in the low 16 bits, optional ReLU
+template <bool RELU> __device__ __forceinline__ uint32_t CvtE4m3x2(float lo, float hi) {
+    unsigned short d;
+    if (RELU) asm("cvt.rn.satfinite.relu.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(d) : "f"(hi), "f"(lo));
+    return (uint32_t)d;
+}
+template <bool RELU> __device__ __forceinline__ uint32_t CvtBf16x2(float lo, float hi) {
+    uint32_t d;
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// y = [relu](acc * scale + bias) for 32 consecutive channels of one row -> packed OutT words (8 for e4m3, 16 for bf16).
+// sc/bi: 32 floats each (registers or shared memory).
+template <typename OutT, bool RELU>
+__device__ __forceinline__ void EpiloguePack32(const uint32_t* acc, const float* sc, const float* bi, uint32_t* out) {
+#pragma unroll
+    for (int q = 0; q < 32; q += 4) {
+        float2 a = Fma2(make_float2(__uint_as_float(acc[q]), __uint_as_float(acc[q + 1])), make_float2(sc[q], sc[q + 1]), make_float2(bi[q], bi[q + 1]));
+        float2 b = Fma2(make_float2(__uint_as_float(acc[q + 2]), __uint_as_float(acc[q + 3])), make_float2(sc[q + 2], sc[q + 3]), make_float2(bi[q + 2], bi[q + 3]));
+        if (sizeof(OutT) == 1) {
+            out[q / 4] = CvtE4m3x2<RELU>(a.x, a.y) | (CvtE4m3x2<RELU>(b.x, b.y) << 16);
+        } else {
+            out[q / 2] = CvtBf16x2<RELU>(a.x, a.y);
+            out[q / 2 + 1] = CvtBf16x2<RELU>(b.x, b.y);
+        }
+    }
+}
+
 __device__ __forceinline__ void PrefetchTensorMap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
