@@ -69,6 +69,10 @@ bool StemNchwSupported(const ConvArgs& a);
 bool Conv3x3TmaSupported(const ConvArgs& a);
 cudaError_t Conv3x3Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
 
+// 1x1/s1 conv with TMA loads/stores and an in-place BN+ReLU transform of the landed A tile (kernels_conv1x1.cu)
+bool Conv1x1TmaSupported(const ConvArgs& a);
+cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
+
 // ---- memory-bound kernels (templated on element type inside) ----
 cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);
 cudaError_t NhwcToNchw(View in, float* out, int n, cudaStream_t stream);

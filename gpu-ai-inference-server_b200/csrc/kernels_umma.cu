@@ -904,6 +904,8 @@ cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t strea
         if (ot == DType::BF16) return LaunchBN<__nv_bfloat16, __nv_bfloat16, kModeStem>(bn, tm, p, stream);
         return LaunchBN<__nv_bfloat16, __nv_fp8_e4m3, kModeStem>(bn, tm, p, stream);
     }
+    static const bool l1tma_enabled = [] { const char* e = getenv("B200_ENGINE_L1TMA"); return !(e && e[0] == '0'); }();
+    if (l1tma_enabled && Conv1x1TmaSupported(a)) return Conv1x1Tma(a, w, stream);
     // 3x3/s1/p1 bottleneck conv: TMA-loaded swizzled patch, nine row-shifted descriptors (kernels_conv3x3.cu)
     static const bool c3tma_enabled = [] { const char* e = getenv("B200_ENGINE_C3TMA"); return !(e && e[0] == '0'); }();
     if (c3tma_enabled && Conv3x3TmaSupported(a)) return Conv3x3Tma(a, w, stream);

@@ -68,6 +68,25 @@ __device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 24)) MbarTimeout();
     }
 }
+#ifndef B200_POLL_SLEEP_NS
+#define B200_POLL_SLEEP_NS 0
+#endif
+// Warp-collective wait (every lane of a CONVERGED warp must call it): lane 0 polls, backing off with nanosleep, the
+// other 31 lanes park at the warp barrier.  Measured on B200: try_wait returns after only ~60-80 cycles when the
+// phase is still pending, so 18 warps x 32 lanes polling at full speed made 30-55 % of all executed instructions
+// SYNCS polls and slowed the working warps down by up to 1.7x.
+__device__ __forceinline__ void MbarWaitWarp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        uint32_t spins = 0;
+        while (!MbarTryWait(bar, parity)) {
+#if B200_POLL_SLEEP_NS > 0
+            __nanosleep(B200_POLL_SLEEP_NS);
+#endif
+            if (++spins > (1u << 24)) MbarTimeout();
+        }
+    }
+    __syncwarp();
+}
 // One lane of a fully converged warp; the compiler keeps the surrounding code on the uniform datapath
 // (descriptors in uniform registers) instead of wrapping every tcgen05/TMA instruction in a waterfall loop.
 __device__ __forceinline__ bool ElectOne() {
@@ -129,6 +148,22 @@ template <int N> __device__ __forceinline__ void BulkWaitRead() { asm volatile("
 template <int N> __device__ __forceinline__ void BulkWait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void NamedBarSync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
+// not volatile, no memory clobber: the compiler may batch these (ordering comes from the mbarrier wait before / the
+// proxy fence after, which are volatile with a memory clobber)
+__device__ __forceinline__ uint4 LdsV4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 LdsF4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void StsV4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- packed epilogue math: two fp32 lanes per instruction, ReLU folded into the narrowing convert
 __device__ __forceinline__ float2 Fma2(float2 a, float2 b, float2 c) {
     float2 d;
@@ -161,6 +196,24 @@ __device__ __forceinline__ void EpiloguePack32(const uint32_t* acc, const float*
     for (int q = 0; q < 32; q += 4) {
         float2 a = Fma2(make_float2(__uint_as_float(acc[q]), __uint_as_float(acc[q + 1])), make_float2(sc[q], sc[q + 1]), make_float2(bi[q], bi[q + 1]));
         float2 b = Fma2(make_float2(__uint_as_float(acc[q + 2]), __uint_as_float(acc[q + 3])), make_float2(sc[q + 2], sc[q + 3]), make_float2(bi[q + 2], bi[q + 3]));
+        if (sizeof(OutT) == 1) {
+            out[q / 4] = CvtE4m3x2<RELU>(a.x, a.y) | (CvtE4m3x2<RELU>(b.x, b.y) << 16);
+        } else {
+            out[q / 2] = CvtBf16x2<RELU>(a.x, a.y);
+            out[q / 2 + 1] = CvtBf16x2<RELU>(b.x, b.y);
+        }
+    }
+}
+
+// Same with scale/bias read from shared memory by 32-bit shared address (explicit LDS.128 broadcasts; going through a
+// generic pointer made the compiler emit generic LD + 12 R2UR per call).
+template <typename OutT, bool RELU>
+__device__ __forceinline__ void EpiloguePack32Smem(const uint32_t* acc, uint32_t sc_addr, uint32_t bi_addr, uint32_t* out) {
+#pragma unroll
+    for (int q = 0; q < 32; q += 4) {
+        const float4 s4 = LdsF4(sc_addr + q * 4), b4 = LdsF4(bi_addr + q * 4);
+        float2 a = Fma2(make_float2(__uint_as_float(acc[q]), __uint_as_float(acc[q + 1])), make_float2(s4.x, s4.y), make_float2(b4.x, b4.y));
+        float2 b = Fma2(make_float2(__uint_as_float(acc[q + 2]), __uint_as_float(acc[q + 3])), make_float2(s4.z, s4.w), make_float2(b4.z, b4.w));
         if (sizeof(OutT) == 1) {
             out[q / 4] = CvtE4m3x2<RELU>(a.x, a.y) | (CvtE4m3x2<RELU>(b.x, b.y) << 16);
         } else {
@@ -245,9 +298,6 @@ __device__ __forceinline__ uint2 LdgNc8(const void* p) {
     uint2 r;
     asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
-}
-__device__ __forceinline__ void StsV4(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // ------------------------------------------------------------------ element traits

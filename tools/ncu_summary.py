@@ -14,7 +14,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 def run(args):
     return subprocess.run(["ncu", "-i", *args], capture_output=True, text=True).stdout
 
-def main(path, top=22):
+def main(path, top=22, dump=None):
     rows = list(csv.reader(io.StringIO(run([path, "--page", "raw", "--csv"]))))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
@@ -32,6 +32,14 @@ def main(path, top=22):
             while j < len(rows) and not (rows[j] and rows[j][0] == 'Kernel Name'):
                 data.append(rows[j]); j += 1
             si, src = hdr.index('# Samples'), hdr.index('Source')
+            if dump:
+                ie, wf = hdr.index('Instructions Executed'), hdr.index('L1 Wavefronts Shared')
+                with open(dump, 'a') as fh:
+                    fh.write(f"## {name}\n#idx\tinst_exec\tsamples\twavefronts_shared\tsass\tstalls\n")
+                    stall_cols = [c for c, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
+                    for k, r in enumerate(data):
+                        st = sorted(((hdr[c][6:], int(r[c])) for c in stall_cols if r[c] not in ('', '0')), key=lambda kv: -kv[1])[:3]
+                        fh.write(f"{k}\t{r[ie] or 0}\t{r[si] or 0}\t{r[wf] or 0}\t{r[src].strip()[:70]}\t{st}\n")
             stall = [c for c, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
             tot = sum(int(r[si] or 0) for r in data)
             print(f"-- stall sites of {name[-70:]} (total samples {tot})")
@@ -44,4 +52,4 @@ def main(path, top=22):
             i += 1
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 22)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 22, sys.argv[3] if len(sys.argv) > 3 else None)
