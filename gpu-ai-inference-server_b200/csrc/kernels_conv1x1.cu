@@ -14,6 +14,8 @@
 //                store per 128-byte column slab (rows past M are clipped by the tensor map).
 // K tail: when Cin is not a multiple of the 128-byte chunk the last box is placed at channel Cin - chunk, i.e. it
 // OVERLAPS the previous chunk (an L2 hit, no extra HBM bytes) and only its last K steps are multiplied.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "umma_ptx.cuh"
 
@@ -24,17 +26,26 @@ namespace {
 
 constexpr int kL1Threads = 32 * 18;
 constexpr int kL1XfWarps = 8, kL1EpiWarps = 8;
-constexpr int kL1MaxCin = 2048;
+constexpr int kL1MaxCin = 1024;
 constexpr int kL1MaxCout = 1024;
+constexpr int kL1ResChunks = 4;  // resident-weight mode: up to 4 K chunks (512 e4m3 / 256 bf16 input channels)
+constexpr int kL1SmemBudget = 226 * 1024;
 
-template <int BN, int OUT_ESZ> struct L1Cfg {
-    static constexpr int kStageBytes = kATileBytes + BN * kRowBytes;
+// RESB: the whole weight matrix (one N tile, <= kL1ResChunks K chunks) is TMA-loaded once per CTA - before the
+// programmatic-dependency wait, so it overlaps the previous kernel - and the pipeline stages carry only A tiles:
+// half the L2->SM traffic per tile and twice the pipeline depth in the same shared memory.
+template <int BN, int OUT_ESZ, bool RESB> struct L1Cfg {
+    static constexpr int kStageBytes = kATileBytes + (RESB ? 0 : BN * kRowBytes);
+    static constexpr int kWBytes = RESB ? kL1ResChunks * BN * kRowBytes : 0;
     static constexpr int kSlabs = BN * OUT_ESZ / 128;            // 128-byte column slabs of the output tile
     static constexpr int kStagingBytes = kSlabs * kTileM * 128;  // one output tile
-    static constexpr int kStages = (BN == 128 && OUT_ESZ == 2) ? 4 : 5;
     static constexpr int kVecBytes = kL1MaxCin * 2 * 2 + kL1MaxCout * 4 * 2;  // packed prologue pairs + fp32 scale/bias
-    static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kStagingBytes + kVecBytes + 512;
+    static constexpr int kFixedBytes = 1024 + kWBytes + 2 * kStagingBytes + kVecBytes + 512;
+    static constexpr int kStagesFit = (kL1SmemBudget - kFixedBytes) / kStageBytes;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+    static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 struct L1Params {
@@ -69,19 +80,20 @@ template <int CH> __device__ __forceinline__ ChunkGeom GeomOf(int c, int Cin) {
     return g;
 }
 
-template <typename MmaT, typename OutT, int BN>
+template <typename MmaT, typename OutT, int BN, bool RESB>
 __global__ void __launch_bounds__(kL1Threads, 1)
 conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in,
                    const __grid_constant__ CUtensorMap tmap_out, const L1Params p) {
     using ME = MmaElem<MmaT>;
-    using Cfg = L1Cfg<BN, (int)sizeof(OutT)>;
+    using Cfg = L1Cfg<BN, (int)sizeof(OutT), RESB>;
     constexpr int NS = Cfg::kStages;
     constexpr int CH = ME::kChunk;
     constexpr int EPV = ME::kPerVec;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* s_staging = smem + NS * Cfg::kStageBytes;
+    uint8_t* s_w = smem + NS * Cfg::kStageBytes;  // resident weights (RESB), 1024-byte aligned
+    uint8_t* s_staging = s_w + Cfg::kWBytes;
     uint32_t* s_pre_scale = reinterpret_cast<uint32_t*>(s_staging + 2 * Cfg::kStagingBytes);  // packed pairs
     uint32_t* s_pre_shift = s_pre_scale + kL1MaxCin / 2;
     float* s_out_scale = reinterpret_cast<float*>(s_pre_shift + kL1MaxCin / 2);
@@ -91,7 +103,8 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     uint64_t* empty_bar = xf_full + NS;
     uint64_t* tmem_full = empty_bar + NS;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* w_bar = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -107,6 +120,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             MbarInit(&tmem_full[a], 1);
             MbarInit(&tmem_empty[a], kL1EpiWarps * 32);
         }
+        MbarInit(w_bar, 1);
         FenceBarrierInit();
         PrefetchTensorMap(&tmap_w);
         PrefetchTensorMap(&tmap_in);
@@ -132,10 +146,18 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
     if (warp == 0) {
         // =========================================================== TMA producer
+        const ChunkGeom gt = GeomOf<CH>(p.num_chunks - 1, p.Cin);  // only the last chunk can be irregular
+        if (RESB) {  // weights do not depend on the previous kernel: load them before the dependency wait
+            if (ElectOne()) {
+                MbarArriveExpectTx(w_bar, (uint32_t)(p.num_chunks * BN * kRowBytes));
+                for (int c = 0; c < p.num_chunks; ++c)
+                    TmaLoad2D(s_w + c * BN * kRowBytes, &tmap_w, w_bar, c == p.num_chunks - 1 ? gt.ch_base : c * CH, 0);
+            }
+            __syncwarp();
+        }
         GridDepWait();
         int stage = 0;
         uint32_t phase = 0;
-        const ChunkGeom gt = GeomOf<CH>(p.num_chunks - 1, p.Cin);  // only the last chunk can be irregular
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
             for (int c = 0; c < p.num_chunks; ++c) {
@@ -145,7 +167,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
                     MbarArriveExpectTx(&raw_full[stage], (uint32_t)Cfg::kStageBytes);
                     TmaLoad2D(a_dst, &tmap_in, &raw_full[stage], p.in_coff + ch_base, m_tile * kTileM);
-                    TmaLoad2D(a_dst + kATileBytes, &tmap_w, &raw_full[stage], ch_base, n_tile * BN);
+                    if (!RESB) TmaLoad2D(a_dst + kATileBytes, &tmap_w, &raw_full[stage], ch_base, n_tile * BN);
                 }
                 __syncwarp();
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -161,6 +183,8 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         const int t_lo = gt.k_lo / ME::kStepK, t_hi = gt.k_hi / ME::kStepK;
         int stage = 0;
         uint32_t phase = 0, tile_iter = 0;
+        const uint64_t w_desc = MakeSmemDesc(SmemAddr(s_w));
+        if (RESB) MbarWaitWarp(w_bar, 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
             const uint32_t acc = tile_iter & 1u, acc_phase = (tile_iter >> 1) & 1u;
             MbarWaitWarp(&tmem_empty[acc], acc_phase ^ 1u);
@@ -170,7 +194,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 const bool last = c == p.num_chunks - 1;
                 const int ks_lo = last ? t_lo : 0, ks_hi = last ? t_hi : CH / ME::kStepK;
                 const uint64_t a_desc = stage_desc + (uint64_t)((uint32_t)stage * (Cfg::kStageBytes >> 4));
-                const uint64_t b_desc = a_desc + (uint64_t)(kATileBytes >> 4);
+                const uint64_t b_desc = RESB ? w_desc + (uint64_t)((uint32_t)c * (BN * kRowBytes >> 4)) : a_desc + (uint64_t)(kATileBytes >> 4);
                 MbarWaitWarp(&ready[stage], phase);
                 TcFenceAfter();
                 if (ElectOne()) {
@@ -323,10 +347,10 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
 }
 
-template <typename MmaT, typename OutT, int BN>
+template <typename MmaT, typename OutT, int BN, bool RESB>
 cudaError_t LaunchL1(const CUtensorMap& tw, const CUtensorMap& tin, const CUtensorMap& tout, const L1Params& p, cudaStream_t stream) {
-    using Cfg = L1Cfg<BN, (int)sizeof(OutT)>;
-    auto kern = conv1x1_tma_kernel<MmaT, OutT, BN>;
+    using Cfg = L1Cfg<BN, (int)sizeof(OutT), RESB>;
+    auto kern = conv1x1_tma_kernel<MmaT, OutT, BN, RESB>;
     static int sm_count[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -396,12 +420,17 @@ cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
     const CUtensorMap& tw = *reinterpret_cast<const CUtensorMap*>(w.tensor_map);
     const CUtensorMap& ti = *reinterpret_cast<const CUtensorMap*>(&tin);
     const CUtensorMap& to = *reinterpret_cast<const CUtensorMap*>(&tout);
+    static const bool resb_enabled = [] { const char* e = getenv("B200_ENGINE_RESB"); return !(e && e[0] == '0'); }();
+    const bool resb = resb_enabled && p.num_n_tiles == 1 && p.num_chunks <= kL1ResChunks;
     if (it == DType::BF16) {
-        if (bn == 128) return LaunchL1<__nv_bfloat16, __nv_bfloat16, 128>(tw, ti, to, p, stream);
-        return LaunchL1<__nv_bfloat16, __nv_bfloat16, 64>(tw, ti, to, p, stream);
+        if (bn == 128) return resb ? LaunchL1<__nv_bfloat16, __nv_bfloat16, 128, true>(tw, ti, to, p, stream)
+                                   : LaunchL1<__nv_bfloat16, __nv_bfloat16, 128, false>(tw, ti, to, p, stream);
+        return resb ? LaunchL1<__nv_bfloat16, __nv_bfloat16, 64, true>(tw, ti, to, p, stream)
+                    : LaunchL1<__nv_bfloat16, __nv_bfloat16, 64, false>(tw, ti, to, p, stream);
     }
     if (bn != 128) return cudaErrorInvalidValue;
-    return LaunchL1<__nv_fp8_e4m3, __nv_fp8_e4m3, 128>(tw, ti, to, p, stream);
+    return resb ? LaunchL1<__nv_fp8_e4m3, __nv_fp8_e4m3, 128, true>(tw, ti, to, p, stream)
+                : LaunchL1<__nv_fp8_e4m3, __nv_fp8_e4m3, 128, false>(tw, ti, to, p, stream);
 }
 
 }  // namespace kernels
