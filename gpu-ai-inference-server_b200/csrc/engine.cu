@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
@@ -191,8 +192,92 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
         }
         pr.umma.tensor_map = tm;
     }
+    BuildDenseRuns();
     flush_bytes_ = 256u << 20;
     CudaCheck(cudaStreamSynchronize(stream_), "replica init");
+}
+
+// Finds maximal runs of dense layers (conv1x1 -> 128 channels -> conv3x3 -> 32 channels appended to the buffer the 1x1
+// read) whose images are small enough for a CTA to own whole images, and builds the device-side layer tables of the
+// dense-block kernel.  e4m3 mode only; everything else keeps the layer-per-kernel schedule.
+void Replica::BuildDenseRuns() {
+    const Plan& P = *plan_;
+    if (P.precision != Precision::FP8) return;
+    if (const char* e = getenv("B200_ENGINE_DENSEFUSE")) if (e[0] == '0') return;
+    auto readers = [&](int tensor) {
+        int c = 0;
+        for (const Step& s : P.steps) c += (s.in == tensor) + (s.in2 == tensor);
+        for (int o : P.outputs) c += (o == tensor);
+        return c;
+    };
+    auto pair_ok = [&](size_t i) -> bool {
+        if (i + 1 >= P.steps.size()) return false;
+        const Step& a = P.steps[i];
+        const Step& b = P.steps[i + 1];
+        if (a.kind != StepKind::Conv || b.kind != StepKind::Conv) return false;
+        const Prepared& pa = prepared_[i];
+        const Prepared& pb = prepared_[i + 1];
+        if (!pa.use_umma || !pb.use_umma || !pa.umma.tensor_map || !pb.umma.tensor_map) return false;
+        if (a.R != 1 || a.S != 1 || a.stride != 1 || a.pad != 0 || a.pool2_fused || a.stem_nchw || a.pre_scale < 0) return false;
+        if (b.R != 3 || b.S != 3 || b.stride != 1 || b.pad != 1 || b.pool2_fused || b.pre_scale >= 0) return false;
+        if (a.Cout != 128 || b.Cin != 128 || b.Cout != 32 || a.Cin % 32 != 0 || a.Cin < 32 || a.Cin > 2048) return false;
+        if (b.in != a.out || readers(a.out) != 1) return false;
+        const TensorDesc& ain = P.tensors[a.in];
+        const TensorDesc& bout = P.tensors[b.out];
+        if (ain.dtype != DType::FP8 || bout.dtype != DType::FP8 || P.tensors[a.out].dtype != DType::FP8) return false;
+        if (ain.buffer != bout.buffer || ain.pitch != bout.pitch || ain.c_off != 0 || bout.c_off != a.Cin) return false;
+        if (ain.H != bout.H || ain.W != bout.W || ain.pitch % 16 != 0) return false;
+        int ipc = 0, mt = 0;
+        return kernels::DenseBlockGeometry(ain.H, ain.W, &ipc, &mt);
+    };
+    for (size_t i = 0; i < P.steps.size();) {
+        if (!pair_ok(i)) { ++i; continue; }
+        const TensorDesc& first_in = P.tensors[P.steps[i].in];
+        size_t j = i;
+        std::vector<kernels::DenseLayerDesc> table;
+        while (pair_ok(j)) {
+            const Step& a = P.steps[j];
+            const Step& b = P.steps[j + 1];
+            const TensorDesc& ain = P.tensors[a.in];
+            if (ain.buffer != first_in.buffer || ain.H != first_in.H || ain.W != first_in.W || ain.pitch != first_in.pitch) break;
+            kernels::DenseLayerDesc d;
+            memset(&d, 0, sizeof(d));
+            memcpy(&d.w1, prepared_[j].umma.tensor_map, sizeof(CUtensorMap));
+            memcpy(&d.w2, prepared_[j + 1].umma.tensor_map, sizeof(CUtensorMap));
+            // folded BN1 as packed f16x2 pairs (the transform warps' arithmetic type in e4m3 mode)
+            const std::vector<float>& sc = P.consts[a.pre_scale].data;
+            const std::vector<float>& sh = P.consts[a.pre_shift].data;
+            std::vector<uint32_t> psc((a.Cin + 1) / 2 + 8, 0), psh((a.Cin + 1) / 2 + 8, 0);
+            for (int c = 0; c < a.Cin; ++c) {
+                const uint32_t hs = __half_as_ushort(__float2half_rn(sc[c])), ht = __half_as_ushort(__float2half_rn(sh[c]));
+                psc[c / 2] |= hs << (16 * (c & 1));
+                psh[c / 2] |= ht << (16 * (c & 1));
+            }
+            d.pre_scale = (const uint32_t*)Upload(psc.data(), psc.size() * 4);
+            d.pre_shift = (const uint32_t*)Upload(psh.data(), psh.size() * 4);
+            d.s1 = prepared_[j].umma.out_scale;
+            d.b1 = prepared_[j].conv.bias;
+            d.s2 = prepared_[j + 1].umma.out_scale;
+            d.b2 = prepared_[j + 1].conv.bias;
+            d.Cin = a.Cin;
+            d.c_off_out = P.tensors[b.out].c_off;
+            d.pre_relu = a.pre_relu; d.relu1 = a.post_relu; d.relu2 = b.post_relu;
+            table.push_back(d);
+            j += 2;
+        }
+        if (table.empty()) { ++i; continue; }
+        DenseRun run;
+        run.first_step = i;
+        run.num_layers = (int)table.size();
+        run.args.layers_dev = (const kernels::DenseLayerDesc*)Upload(table.data(), table.size() * sizeof(kernels::DenseLayerDesc));
+        run.args.num_layers = run.num_layers;
+        run.args.buf = BufferPtr(first_in.buffer);
+        run.args.pitch = first_in.pitch;
+        run.args.H = first_in.H; run.args.W = first_in.W;
+        prepared_[i].fused_run = (int)dense_runs_.size();
+        dense_runs_.push_back(run);
+        i = j;
+    }
 }
 
 Replica::~Replica() {
@@ -271,10 +356,24 @@ void Replica::EnqueueStep(size_t i, int n, int off) {
     if (e != cudaSuccess) CudaCheck(e, ("step '" + s.name + "' (" + StepKindName(s.kind) + ")").c_str());
 }
 
+size_t Replica::EnqueueAt(size_t i, int n, int off) {
+    const int r = prepared_[i].fused_run;
+    if (r < 0) {
+        EnqueueStep(i, n, off);
+        return 1;
+    }
+    DenseRun& run = dense_runs_[r];
+    kernels::DenseBlockArgs a = run.args;
+    a.n = n;
+    cudaError_t e = kernels::DenseBlockFp8(a, stream_);
+    if (e != cudaSuccess) CudaCheck(e, ("dense block starting at step '" + plan_->steps[i].name + "'").c_str());
+    return (size_t)run.num_layers * 2;
+}
+
 void Replica::Enqueue(int n, int off) {
     if (n <= 0 || off < 0 || off + n > plan_->max_batch) throw CudaError("batch " + std::to_string(off + n) + " exceeds the planned maximum");
     if (!use_graphs_) {
-        for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n, off);
+        for (size_t i = 0; i < plan_->steps.size();) i += EnqueueAt(i, n, off);
         return;
     }
     const int64_t key = ((int64_t)off << 20) | (int64_t)n;
@@ -284,7 +383,7 @@ void Replica::Enqueue(int n, int off) {
         uint64_t before = kernels::LaunchCount();
         CudaCheck(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
         try {
-            for (size_t i = 0; i < plan_->steps.size(); ++i) EnqueueStep(i, n, off);
+            for (size_t i = 0; i < plan_->steps.size();) i += EnqueueAt(i, n, off);
         } catch (...) {
             cudaStreamEndCapture(stream_, &graph);
             if (graph) cudaGraphDestroy(graph);
@@ -399,9 +498,10 @@ std::string Replica::ProfileSteps(int n, int repeats) {
     repeats = std::max(1, repeats);
     for (int r = 0; r < repeats + 1; ++r) {  // first pass is warm-up
         CudaCheck(cudaEventRecord(ev[0], stream_), "event");
-        for (size_t i = 0; i < ns; ++i) {
-            EnqueueStep(i, n);
-            CudaCheck(cudaEventRecord(ev[i + 1], stream_), "event");
+        for (size_t i = 0; i < ns;) {  // a fused run is timed as one step (its remaining steps read 0)
+            const size_t used = EnqueueAt(i, n, 0);
+            for (size_t u = 0; u < used; ++u) CudaCheck(cudaEventRecord(ev[i + u + 1], stream_), "event");
+            i += used;
         }
         CudaCheck(cudaStreamSynchronize(stream_), "profile sync");
         if (r == 0) continue;

@@ -56,12 +56,21 @@ private:
         const float* scale = nullptr;
         const float* shift = nullptr;
         size_t in_io_stride = 0, in2_io_stride = 0, out_io_stride = 0;  // bytes per sample when the view is graph I/O
+        int fused_run = -1;  // index into dense_runs_ when this step starts a run executed by the dense-block kernel
+    };
+    // Consecutive (1x1 conv, 3x3 conv) step pairs of one dense block executed by ONE persistent kernel.
+    struct DenseRun {
+        size_t first_step = 0;
+        int num_layers = 0;
+        kernels::DenseBlockArgs args;
     };
 
     // Every step on stream_ for samples [off, off+n) of the staged batch (captured into a graph when enabled).
     // Only graph-input / graph-output buffers are indexed by `off`; all intermediate buffers are reused.
     void Enqueue(int n, int off = 0);
     void EnqueueStep(size_t i, int n, int off = 0);
+    size_t EnqueueAt(size_t i, int n, int off);  // runs step i (or the fused run starting there); returns steps consumed
+    void BuildDenseRuns();
     kernels::View MakeView(int tensor) const;
     void* BufferPtr(int buffer) const;
     void* Upload(const void* host, size_t bytes);
@@ -80,6 +89,7 @@ private:
     std::vector<void*> allocations_;
     std::vector<const float*> dconst_;  // fp32 device copy of every Plan::consts entry that is used as a vector
     std::vector<Prepared> prepared_;
+    std::vector<DenseRun> dense_runs_;
     std::map<int64_t, cudaGraphExec_t> graphs_;  // key: (off << 20) | n
     std::map<int64_t, int> graph_launches_;  // kernels per captured forward, for the launch counter
     int launches_per_forward_ = 0;

@@ -73,6 +73,29 @@ cudaError_t Conv3x3Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
 bool Conv1x1TmaSupported(const ConvArgs& a);
 cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
 
+// ---- a whole dense block in one persistent kernel (kernels_dense.cu; e4m3, whole images per CTA) ----
+struct DenseLayerDesc {          // one BN-ReLU-Conv1x1(->128)-BN-ReLU-Conv3x3(->32) layer; lives in device memory
+    TensorMap w1;                // conv1 weights [128][K_pad] e4m3, box {128, 128}, SWIZZLE_128B
+    TensorMap w2;                // conv2 weights [32][9*128] e4m3, box {128, 32}, SWIZZLE_128B
+    const uint32_t* pre_scale;   // folded BN1 scale/shift as packed f16x2 pairs, Cin/2 words each
+    const uint32_t* pre_shift;
+    const float* s1;             // conv1 epilogue: per-channel dequant scale, bias (BN2 folded) [128]
+    const float* b1;
+    const float* s2;             // conv2 epilogue [32]
+    const float* b2;
+    int Cin, c_off_out;          // input channels [0, Cin); the 32 outputs go to channels [c_off_out, c_off_out + 32)
+    int pre_relu, relu1, relu2;
+    int pad_[3];
+};
+struct DenseBlockArgs {
+    const DenseLayerDesc* layers_dev = nullptr;
+    int num_layers = 0;
+    void* buf = nullptr;         // block buffer (NHWC e4m3), channel offset 0 of the first layer's input
+    int pitch = 0, n = 0, H = 0, W = 0;
+};
+bool DenseBlockGeometry(int H, int W, int* images_per_cta, int* m_tiles);
+cudaError_t DenseBlockFp8(const DenseBlockArgs& a, cudaStream_t stream);
+
 // ---- memory-bound kernels (templated on element type inside) ----
 cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);
 cudaError_t NhwcToNchw(View in, float* out, int n, cudaStream_t stream);

@@ -107,18 +107,23 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Role map: the two single-thread roles sit on the HIGHEST warp ids.  The SM's issue arbiter prefers the highest
+    // warp id of an SMSP (measured timeline: with the MMA issuer on warp 1 it was starved for ~1 us by the poll loops of
+    // higher-numbered waiting warps - a priority inversion, since those warps were waiting for the MMA).
+    constexpr int kNW = kL1Threads / 32;
+    const int wrole = warp >= kNW - 2 ? warp - (kNW - 2) : warp + 2;  // 0 TMA, 1 MMA, 2.. transform, then epilogue
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const bool has_pre = p.pre_scale != nullptr;
 
-    if (warp == 0 && lane == 0) {
+    if (wrole == 0 && lane == 0) {
         for (int s = 0; s < NS; ++s) {
             MbarInit(&raw_full[s], 1);
-            MbarInit(&xf_full[s], kL1XfWarps * 32);
+            MbarInit(&xf_full[s], kL1XfWarps);
             MbarInit(&empty_bar[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             MbarInit(&tmem_full[a], 1);
-            MbarInit(&tmem_empty[a], kL1EpiWarps * 32);
+            MbarInit(&tmem_empty[a], kL1EpiWarps);
         }
         MbarInit(w_bar, 1);
         FenceBarrierInit();
@@ -126,7 +131,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         PrefetchTensorMap(&tmap_in);
         PrefetchTensorMap(&tmap_out);
     }
-    if (warp == 1) TmemAlloc(tmem_slot, Cfg::kTmemCols);
+    if (wrole == 1) TmemAlloc(tmem_slot, Cfg::kTmemCols);
     if (has_pre) {
         for (int i = threadIdx.x; i < (p.Cin + 1) / 2; i += kL1Threads) {
             const int c0 = 2 * i, c1 = 2 * i + 1;
@@ -144,7 +149,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const uint32_t tmem_base = *tmem_slot;
     GridDepLaunch();
 
-    if (warp == 0) {
+    if (wrole == 0) {
         // =========================================================== TMA producer
         const ChunkGeom gt = GeomOf<CH>(p.num_chunks - 1, p.Cin);  // only the last chunk can be irregular
         if (RESB) {  // weights do not depend on the previous kernel: load them before the dependency wait
@@ -173,7 +178,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 1) {
+    } else if (wrole == 1) {
         // =========================================================== MMA issuer
         constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, BN);
         const uint64_t stage_desc = MakeSmemDesc(SmemAddr(smem));
@@ -209,10 +214,10 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp < 2 + kL1XfWarps) {
+    } else if (wrole < 2 + kL1XfWarps) {
         // =========================================================== transform warps: in-place BN + ReLU on the A tile
         if (has_pre) {
-            const int tw = warp - 2;
+            const int tw = wrole - 2;
             constexpr int kPairs = EPV / 2;
             constexpr int kMaxU = 4;  // (32 rows x one 16-byte piece) units per warp and chunk
             // Full chunks: this warp owns piece `tw` of all 128 rows.  The (possibly partial) last chunk has vp < 8 valid
@@ -277,21 +282,22 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                             if (ch_tail[i] >= 0) StsV4(a_base + off_tail[i], v[i]);
                     }
                     FenceProxyAsync();
-                    MbarArrive(&xf_full[stage]);
+                    __syncwarp();
+                    if (lane == 0) MbarArrive(&xf_full[stage]);  // one arrive per warp (per-thread arrives serialise on the barrier word)
                     if (++stage == NS) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else {
         // =========================================================== epilogue
-        const int ew = warp - (2 + kL1XfWarps);
+        const int ew = wrole - (2 + kL1XfWarps);
         const int q = warp & 3;             // TMEM lane quarter this warp may access
         const int h = ew >> 2;              // which half of the column groups
         constexpr int kCgs = BN / 32;       // 32-column groups per tile
         constexpr int kCgPerWarp = kCgs >= 2 ? kCgs / 2 : 1;
         constexpr int kOutB = (int)sizeof(OutT);
         constexpr int kPiecesPerCg = 32 * kOutB / 16;  // 16-byte pieces per row of one column group
-        const bool leader = (warp == 2 + kL1XfWarps) && lane == 0;
+        const bool leader = (wrole == 2 + kL1XfWarps) && lane == 0;
         const int row = q * 32 + lane;
         if (leader) GridDepWait();
         uint32_t tile_iter = 0;
@@ -326,7 +332,8 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 }
             }
             TcFenceBefore();
-            MbarArrive(&tmem_empty[acc]);
+            __syncwarp();
+            if (lane == 0) MbarArrive(&tmem_empty[acc]);
             FenceProxyAsync();  // staging writes -> visible to the TMA store
             NamedBarSync(2, kL1EpiWarps * 32);
             if (leader) {
@@ -341,7 +348,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
     TcFenceBefore();
     __syncthreads();
-    if (warp == 1) {
+    if (wrole == 1) {
         TcFenceAfter();
         TmemDealloc(tmem_base, Cfg::kTmemCols);
     }
