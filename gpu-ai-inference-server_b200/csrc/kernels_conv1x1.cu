@@ -34,18 +34,24 @@ constexpr int kL1SmemBudget = 226 * 1024;
 // RESB: the whole weight matrix (one N tile, <= kL1ResChunks K chunks) is TMA-loaded once per CTA - before the
 // programmatic-dependency wait, so it overlaps the previous kernel - and the pipeline stages carry only A tiles:
 // half the L2->SM traffic per tile and twice the pipeline depth in the same shared memory.
-template <int BN, int OUT_ESZ, bool RESB> struct L1Cfg {
-    static constexpr int kStageBytes = kATileBytes + (RESB ? 0 : BN * kRowBytes);
+// POOL (transition layers): the 2x2 average pool that follows the 1x1 conv is commuted in front of it (both are linear);
+// a stage then carries FOUR raw planes - the (dy, dx) pixels of every output pixel, each landed by its own 5-D TMA box -
+// and the transform warps write sum(relu(bn(x))) over the four planes into plane 0, the A operand.
+template <int BN, int OUT_ESZ, bool RESB, bool POOL> struct L1Cfg {
+    static constexpr int kAPlanes = POOL ? 4 : 1;
+    static constexpr int kABytes = kAPlanes * kATileBytes;
+    static constexpr int kStageBytes = kABytes + (RESB ? 0 : BN * kRowBytes);
     static constexpr int kWBytes = RESB ? kL1ResChunks * BN * kRowBytes : 0;
     static constexpr int kSlabs = BN * OUT_ESZ / 128;            // 128-byte column slabs of the output tile
     static constexpr int kStagingBytes = kSlabs * kTileM * 128;  // one output tile
     static constexpr int kVecBytes = kL1MaxCin * 2 * 2 + kL1MaxCout * 4 * 2;  // packed prologue pairs + fp32 scale/bias
-    static constexpr int kFixedBytes = 1024 + kWBytes + 2 * kStagingBytes + kVecBytes + 512;
+    static constexpr int kStagingBufs = (POOL && OUT_ESZ == 2) ? 1 : 2;  // output tiles in flight towards the TMA store
+    static constexpr int kFixedBytes = 1024 + kWBytes + kStagingBufs * kStagingBytes + kVecBytes + 512;
     static constexpr int kStagesFit = (kL1SmemBudget - kFixedBytes) / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
     static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
-    static_assert(kStages >= 3, "pipeline too shallow");
+    static_assert(kStages >= 2, "pipeline too shallow");
 };
 
 struct L1Params {
@@ -57,6 +63,9 @@ struct L1Params {
     int in_coff, out_coff;  // element offsets of the channel slices
     int Cin, Cout, M;
     int num_m_tiles, num_n_tiles, num_chunks;
+    int tile_rows;        // output pixels per M tile (128, or k*Wo whole output rows in POOL mode)
+    int pool_k;           // POOL: output rows per M tile
+    float out_scale_mul;  // POOL: 0.25 (the average), folded into the epilogue scale
 };
 
 // Chunk geometry shared by the producer, the transform warps and the MMA issuer.
@@ -80,12 +89,12 @@ template <int CH> __device__ __forceinline__ ChunkGeom GeomOf(int c, int Cin) {
     return g;
 }
 
-template <typename MmaT, typename OutT, int BN, bool RESB>
+template <typename MmaT, typename OutT, int BN, bool RESB, bool POOL>
 __global__ void __launch_bounds__(kL1Threads, 1)
 conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in,
                    const __grid_constant__ CUtensorMap tmap_out, const L1Params p) {
     using ME = MmaElem<MmaT>;
-    using Cfg = L1Cfg<BN, (int)sizeof(OutT), RESB>;
+    using Cfg = L1Cfg<BN, (int)sizeof(OutT), RESB, POOL>;
     constexpr int NS = Cfg::kStages;
     constexpr int CH = ME::kChunk;
     constexpr int EPV = ME::kPerVec;
@@ -94,7 +103,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem + NS * Cfg::kStageBytes;  // resident weights (RESB), 1024-byte aligned
     uint8_t* s_staging = s_w + Cfg::kWBytes;
-    uint32_t* s_pre_scale = reinterpret_cast<uint32_t*>(s_staging + 2 * Cfg::kStagingBytes);  // packed pairs
+    uint32_t* s_pre_scale = reinterpret_cast<uint32_t*>(s_staging + Cfg::kStagingBufs * Cfg::kStagingBytes);  // packed pairs
     uint32_t* s_pre_shift = s_pre_scale + kL1MaxCin / 2;
     float* s_out_scale = reinterpret_cast<float*>(s_pre_shift + kL1MaxCin / 2);
     float* s_bias = s_out_scale + kL1MaxCout;
@@ -140,7 +149,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         }
     }
     for (int i = threadIdx.x; i < p.num_n_tiles * BN; i += kL1Threads) {
-        s_out_scale[i] = i < p.Cout ? p.out_scale[i] : 0.f;
+        s_out_scale[i] = i < p.Cout ? p.out_scale[i] * p.out_scale_mul : 0.f;
         s_bias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
     }
     TcFenceBefore();
@@ -170,9 +179,16 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 if (ElectOne()) {
                     const int ch_base = c == p.num_chunks - 1 ? gt.ch_base : c * CH;
                     uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
-                    MbarArriveExpectTx(&raw_full[stage], (uint32_t)Cfg::kStageBytes);
-                    TmaLoad2D(a_dst, &tmap_in, &raw_full[stage], p.in_coff + ch_base, m_tile * kTileM);
-                    if (!RESB) TmaLoad2D(a_dst + kATileBytes, &tmap_w, &raw_full[stage], ch_base, n_tile * BN);
+                    if (POOL) {
+                        MbarArriveExpectTx(&raw_full[stage], (uint32_t)(4 * p.tile_rows * kRowBytes + (RESB ? 0 : BN * kRowBytes)));
+#pragma unroll
+                        for (int pl = 0; pl < 4; ++pl)
+                            TmaLoad5D(a_dst + pl * kATileBytes, &tmap_in, &raw_full[stage], p.in_coff + ch_base, 0, m_tile * p.pool_k, pl & 1, pl >> 1);
+                    } else {
+                        MbarArriveExpectTx(&raw_full[stage], (uint32_t)Cfg::kStageBytes);
+                        TmaLoad2D(a_dst, &tmap_in, &raw_full[stage], p.in_coff + ch_base, m_tile * kTileM);
+                    }
+                    if (!RESB) TmaLoad2D(a_dst + Cfg::kABytes, &tmap_w, &raw_full[stage], ch_base, n_tile * BN);
                 }
                 __syncwarp();
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -199,7 +215,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 const bool last = c == p.num_chunks - 1;
                 const int ks_lo = last ? t_lo : 0, ks_hi = last ? t_hi : CH / ME::kStepK;
                 const uint64_t a_desc = stage_desc + (uint64_t)((uint32_t)stage * (Cfg::kStageBytes >> 4));
-                const uint64_t b_desc = RESB ? w_desc + (uint64_t)((uint32_t)c * (BN * kRowBytes >> 4)) : a_desc + (uint64_t)(kATileBytes >> 4);
+                const uint64_t b_desc = RESB ? w_desc + (uint64_t)((uint32_t)c * (BN * kRowBytes >> 4)) : a_desc + (uint64_t)(Cfg::kABytes >> 4);
                 MbarWaitWarp(&ready[stage], phase);
                 TcFenceAfter();
                 if (ElectOne()) {
@@ -256,7 +272,23 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                     const uint32_t a_base = smem_base + stage * Cfg::kStageBytes;
                     MbarWaitWarp(&raw_full[stage], phase);
                     uint4 v[kMaxU];
-                    if (!(tail_partial && c == p.num_chunks - 1)) {
+                    if (POOL) {
+                        // four raw planes -> plane 0 (all chunks are full in POOL mode); two units at a time (8 loads in flight)
+                        load_consts(c * CH + tw * EPV);
+#pragma unroll
+                        for (int i = 0; i < kMaxU; i += 2) {
+                            uint4 q[2][4];
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                                for (int pl = 0; pl < 4; ++pl) q[j][pl] = LdsV4(a_base + pl * kATileBytes + off_full[i + j]);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                v[j] = p.pre_relu ? PoolPiece<MmaT, true>(q[j], sc, sh) : PoolPiece<MmaT, false>(q[j], sc, sh);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) StsV4(a_base + off_full[i + j], v[j]);
+                        }
+                    } else if (!(tail_partial && c == p.num_chunks - 1)) {
                         // all loads first, then the math, then the stores: four independent dependency chains in flight
 #pragma unroll
                         for (int i = 0; i < kMaxU; ++i) v[i] = LdsV4(a_base + off_full[i]);
@@ -304,8 +336,11 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_iter) {
             const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
             const uint32_t acc = tile_iter & 1u, acc_phase = (tile_iter >> 1) & 1u;
-            uint8_t* stg = s_staging + acc * Cfg::kStagingBytes;
-            if (leader) BulkWaitRead<1>();  // the store that read this staging buffer two tiles ago is done
+            uint8_t* stg = s_staging + (Cfg::kStagingBufs == 2 ? acc : 0u) * Cfg::kStagingBytes;
+            if (leader) {  // the store that last read this staging buffer is done
+                if (Cfg::kStagingBufs == 2) BulkWaitRead<1>();
+                else BulkWaitRead<0>();
+            }
             NamedBarSync(1, kL1EpiWarps * 32);
             MbarWaitWarp(&tmem_full[acc], acc_phase);
             TcFenceAfter();
@@ -339,7 +374,7 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             if (leader) {
 #pragma unroll
                 for (int s = 0; s < Cfg::kSlabs; ++s)
-                    TmaStore2D(&tmap_out, stg + s * (kTileM * 128), p.out_coff + n_tile * BN + s * (128 / kOutB), m_tile * kTileM);
+                    TmaStore2D(&tmap_out, stg + s * (kTileM * 128), p.out_coff + n_tile * BN + s * (128 / kOutB), m_tile * p.tile_rows);
                 BulkCommit();
             }
         }
@@ -354,10 +389,10 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     }
 }
 
-template <typename MmaT, typename OutT, int BN, bool RESB>
+template <typename MmaT, typename OutT, int BN, bool RESB, bool POOL = false>
 cudaError_t LaunchL1(const CUtensorMap& tw, const CUtensorMap& tin, const CUtensorMap& tout, const L1Params& p, cudaStream_t stream) {
-    using Cfg = L1Cfg<BN, (int)sizeof(OutT), RESB>;
-    auto kern = conv1x1_tma_kernel<MmaT, OutT, BN, RESB>;
+    using Cfg = L1Cfg<BN, (int)sizeof(OutT), RESB, POOL>;
+    auto kern = conv1x1_tma_kernel<MmaT, OutT, BN, RESB, POOL>;
     static int sm_count[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -381,8 +416,13 @@ cudaError_t LaunchL1(const CUtensorMap& tw, const CUtensorMap& tin, const CUtens
 bool Conv1x1TmaSupported(const ConvArgs& a) {
     const DType it = a.in.dtype, ot = a.out.dtype;
     if (it != ot || (it != DType::BF16 && it != DType::FP8)) return false;
-    if (!(a.R == 1 && a.S == 1 && a.stride == 1 && a.pad == 0) || a.pool2 || a.stem_nchw) return false;
+    if (!(a.R == 1 && a.S == 1 && a.stride == 1 && a.pad == 0) || a.stem_nchw) return false;
     const int esz = (int)DTypeSize(it);
+    if (a.pool2) {  // transition: whole 128-byte chunks, a prologue, even images, N tile 128, at least one output row per tile
+        if (a.Cin % (128 / esz) != 0 || !a.pre_scale || a.in.H != 2 * a.out.H || a.in.W != 2 * a.out.W || a.out.W > 128 || a.Cout % 128 != 0) return false;
+    } else if (a.in.H != a.out.H || a.in.W != a.out.W) {
+        return false;
+    }
     const int step_k = 32 / esz, slab = 128 / esz;
     if (a.Cin % step_k != 0 || a.Cin > kL1MaxCin || a.Cin < step_k) return false;
     if (a.Cout % slab != 0 || a.Cout > kL1MaxCout) return false;  // whole 128-byte slabs per TMA store
@@ -392,7 +432,7 @@ bool Conv1x1TmaSupported(const ConvArgs& a) {
     if (reinterpret_cast<uintptr_t>(a.in.base) % 16 != 0 || reinterpret_cast<uintptr_t>(a.out.base) % 16 != 0) return false;
     // a short single chunk reads a whole 128-byte box: it must stay inside the pixel (values past Cin are never multiplied)
     if (a.Cin < slab && a.in.c_off + slab > a.in.pitch) return false;
-    return a.in.H == a.out.H && a.in.W == a.out.W;
+    return true;
 }
 
 cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream) {
@@ -408,11 +448,25 @@ cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
     p.M = a.n * a.out.H * a.out.W;
     if (p.M <= 0) return cudaSuccess;
     const int bn = a.Cout <= 64 ? 64 : 128;
-    p.num_m_tiles = (p.M + kTileM - 1) / kTileM;
     p.num_n_tiles = a.Cout / bn;
     p.num_chunks = (a.Cin + ch - 1) / ch;
+    p.tile_rows = kTileM; p.pool_k = 0; p.out_scale_mul = 1.f;
+    p.num_m_tiles = (p.M + kTileM - 1) / kTileM;
     TensorMap tin, tout;
-    {
+    if (a.pool2) {
+        const int Wo = a.out.W, Ho = a.out.H;
+        p.pool_k = kTileM / Wo;
+        if (p.pool_k > 256) p.pool_k = 256;
+        p.tile_rows = p.pool_k * Wo;
+        p.out_scale_mul = 0.25f;
+        p.num_m_tiles = (a.n * Ho + p.pool_k - 1) / p.pool_k;
+        // input as [row pair r = img*Ho + oy][dy][ox][dx][c]: one box = {128 B of channels, Wo, k rows} for a fixed (dx, dy)
+        const uint64_t px = (uint64_t)a.in.pitch * esz;
+        const uint64_t dims[5] = {(uint64_t)a.in.pitch, (uint64_t)Wo, (uint64_t)a.n * Ho, 2, 2};
+        const uint64_t strides[4] = {2 * px, 2 * (uint64_t)a.in.W * px, px, (uint64_t)a.in.W * px};
+        const uint32_t box[5] = {(uint32_t)ch, (uint32_t)Wo, (uint32_t)p.pool_k, 1, 1};
+        if (MakeTensorMap(&tin, a.in.base, esz, 5, dims, strides, box, true) != 0) return cudaErrorInvalidValue;
+    } else {
         const uint64_t dims[2] = {(uint64_t)a.in.pitch, (uint64_t)p.M};
         const uint64_t strides[1] = {(uint64_t)a.in.pitch * esz};
         const uint32_t box[2] = {(uint32_t)ch, (uint32_t)kTileM};
@@ -421,12 +475,17 @@ cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
     {
         const uint64_t dims[2] = {(uint64_t)a.out.pitch, (uint64_t)p.M};
         const uint64_t strides[1] = {(uint64_t)a.out.pitch * esz};
-        const uint32_t box[2] = {(uint32_t)ch, (uint32_t)kTileM};
+        const uint32_t box[2] = {(uint32_t)ch, (uint32_t)p.tile_rows};
         if (MakeTensorMap(&tout, a.out.base, esz, 2, dims, strides, box, true) != 0) return cudaErrorInvalidValue;
     }
     const CUtensorMap& tw = *reinterpret_cast<const CUtensorMap*>(w.tensor_map);
     const CUtensorMap& ti = *reinterpret_cast<const CUtensorMap*>(&tin);
     const CUtensorMap& to = *reinterpret_cast<const CUtensorMap*>(&tout);
+    if (a.pool2) {
+        if (bn != 128) return cudaErrorInvalidValue;
+        if (it == DType::BF16) return LaunchL1<__nv_bfloat16, __nv_bfloat16, 128, false, true>(tw, ti, to, p, stream);
+        return LaunchL1<__nv_fp8_e4m3, __nv_fp8_e4m3, 128, false, true>(tw, ti, to, p, stream);
+    }
     static const bool resb_enabled = [] { const char* e = getenv("B200_ENGINE_RESB"); return !(e && e[0] == '0'); }();
     const bool resb = resb_enabled && p.num_n_tiles == 1 && p.num_chunks <= kL1ResChunks;
     if (it == DType::BF16) {

@@ -137,6 +137,12 @@ __device__ __forceinline__ void TmaLoad4D(void* smem_dst, const CUtensorMap* map
         ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void TmaLoad5D(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 // TMA store of a shared-memory box (bulk async-group completion).
 __device__ __forceinline__ void TmaStore2D(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -411,6 +417,46 @@ template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_fp8_e4m3, true>(
 template <> __device__ __forceinline__ uint4 ProloguePiece<__nv_fp8_e4m3, false>(uint4 v, const uint32_t* sc, const uint32_t* sh) {
     return make_uint4(PrologueWordFp8<false>(v.x, sc, sh), PrologueWordFp8<false>(v.y, sc + 2, sh + 2),
                       PrologueWordFp8<false>(v.z, sc + 4, sh + 4), PrologueWordFp8<false>(v.w, sc + 6, sh + 6));
+}
+
+// Transition layers: A row = SUM over the 2x2 input pixels of relu(x*scale+shift) (the 1/4 of the average is folded into
+// the epilogue scale).  v[0..3] are the same 16-byte piece of the four pixels.
+__device__ __forceinline__ uint32_t AddF16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t AddBf16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+template <typename T, bool RELU> __device__ __forceinline__ uint4 PoolPiece(const uint4* v, const uint32_t* sc, const uint32_t* sh);
+template <bool RELU> __device__ __forceinline__ uint32_t PoolWordFp8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, const uint32_t* sc, const uint32_t* sh) {
+    uint32_t lo = AddF16x2(AddF16x2(FmaF16x2<RELU>(E4m3x2ToF16x2(w0 & 0xFFFFu), sc[0], sh[0]), FmaF16x2<RELU>(E4m3x2ToF16x2(w1 & 0xFFFFu), sc[0], sh[0])),
+                           AddF16x2(FmaF16x2<RELU>(E4m3x2ToF16x2(w2 & 0xFFFFu), sc[0], sh[0]), FmaF16x2<RELU>(E4m3x2ToF16x2(w3 & 0xFFFFu), sc[0], sh[0])));
+    uint32_t hi = AddF16x2(AddF16x2(FmaF16x2<RELU>(E4m3x2ToF16x2(w0 >> 16), sc[1], sh[1]), FmaF16x2<RELU>(E4m3x2ToF16x2(w1 >> 16), sc[1], sh[1])),
+                           AddF16x2(FmaF16x2<RELU>(E4m3x2ToF16x2(w2 >> 16), sc[1], sh[1]), FmaF16x2<RELU>(E4m3x2ToF16x2(w3 >> 16), sc[1], sh[1])));
+    return F16x2ToE4m3x2(lo) | (F16x2ToE4m3x2(hi) << 16);
+}
+template <> __device__ __forceinline__ uint4 PoolPiece<__nv_fp8_e4m3, true>(const uint4* v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(PoolWordFp8<true>(v[0].x, v[1].x, v[2].x, v[3].x, sc, sh), PoolWordFp8<true>(v[0].y, v[1].y, v[2].y, v[3].y, sc + 2, sh + 2),
+                      PoolWordFp8<true>(v[0].z, v[1].z, v[2].z, v[3].z, sc + 4, sh + 4), PoolWordFp8<true>(v[0].w, v[1].w, v[2].w, v[3].w, sc + 6, sh + 6));
+}
+template <> __device__ __forceinline__ uint4 PoolPiece<__nv_fp8_e4m3, false>(const uint4* v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(PoolWordFp8<false>(v[0].x, v[1].x, v[2].x, v[3].x, sc, sh), PoolWordFp8<false>(v[0].y, v[1].y, v[2].y, v[3].y, sc + 2, sh + 2),
+                      PoolWordFp8<false>(v[0].z, v[1].z, v[2].z, v[3].z, sc + 4, sh + 4), PoolWordFp8<false>(v[0].w, v[1].w, v[2].w, v[3].w, sc + 6, sh + 6));
+}
+template <bool RELU> __device__ __forceinline__ uint32_t PoolWordBf16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t sc, uint32_t sh) {
+    return AddBf16x2(AddBf16x2(FmaBf16x2<RELU>(w0, sc, sh), FmaBf16x2<RELU>(w1, sc, sh)), AddBf16x2(FmaBf16x2<RELU>(w2, sc, sh), FmaBf16x2<RELU>(w3, sc, sh)));
+}
+template <> __device__ __forceinline__ uint4 PoolPiece<__nv_bfloat16, true>(const uint4* v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(PoolWordBf16<true>(v[0].x, v[1].x, v[2].x, v[3].x, sc[0], sh[0]), PoolWordBf16<true>(v[0].y, v[1].y, v[2].y, v[3].y, sc[1], sh[1]),
+                      PoolWordBf16<true>(v[0].z, v[1].z, v[2].z, v[3].z, sc[2], sh[2]), PoolWordBf16<true>(v[0].w, v[1].w, v[2].w, v[3].w, sc[3], sh[3]));
+}
+template <> __device__ __forceinline__ uint4 PoolPiece<__nv_bfloat16, false>(const uint4* v, const uint32_t* sc, const uint32_t* sh) {
+    return make_uint4(PoolWordBf16<false>(v[0].x, v[1].x, v[2].x, v[3].x, sc[0], sh[0]), PoolWordBf16<false>(v[0].y, v[1].y, v[2].y, v[3].y, sc[1], sh[1]),
+                      PoolWordBf16<false>(v[0].z, v[1].z, v[2].z, v[3].z, sc[2], sh[2]), PoolWordBf16<false>(v[0].w, v[1].w, v[2].w, v[3].w, sc[3], sh[3]));
 }
 
 __device__ __forceinline__ void CpAsync16(uint32_t dst, const void* src, bool valid) {
