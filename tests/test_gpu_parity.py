@@ -68,8 +68,8 @@ def _conv_node(x, w, out, k, s=1, p=0, bias=None):
                           {"kernel_shape": [k, k], "strides": [s, s], "pads": [p, p, p, p], "dilations": [1, 1], "group": 1})
 
 
-CASES = ["conv1x1_bn_relu", "conv1x1_partial_chunk", "conv3x3", "stem_maxpool", "transition", "dense_block",
-         "dense_block_copy", "cout256", "gap_gemm_softmax"]
+CASES = ["conv1x1_bn_relu", "conv1x1_partial_chunk", "conv1x1_ktail", "conv1x1_long", "conv3x3", "stem_maxpool", "transition",
+         "transition_wide", "dense_block", "dense_block_copy", "dense_block7", "cout256", "gap_gemm_softmax"]
 TOL = {"fp32": 2e-5, "bf16": 2.5e-2, "fp8": 1.5e-1}
 
 
@@ -85,6 +85,13 @@ def _build_case(case, tmp_path, rng):
         inits = {**_bn(rng, 96, "bn"), "w": k(128, 96, 1, 1)}
         nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "y", 1)]
         shp, out = (96, 7, 7), (128, 7, 7)
+    elif case in ("conv1x1_ktail", "conv1x1_long"):
+        # K not a multiple of the 128-byte chunk (overlapped last TMA box); "long" exceeds the resident-weight limit
+        cin = 352 if case == "conv1x1_ktail" else 608
+        inits = {**_bn(rng, cin, "bn"), "w": k(128, cin, 1, 1), "b": rng.normal(0, 0.1, 128)}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1, bias="b"),
+                 onnx_lite.Node("Relu", ["c"], ["y"])]
+        shp, out = (cin, 11, 11), (128, 11, 11)
     elif case == "conv3x3":
         inits = {"w": k(32, 128, 3, 3)}
         nodes = [_conv_node("x", "w", "y", 3, 1, 1)]
@@ -99,17 +106,24 @@ def _build_case(case, tmp_path, rng):
         nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1),
                  onnx_lite.Node("AveragePool", ["c"], ["y"], {"kernel_shape": [2, 2], "strides": [2, 2], "pads": [0, 0, 0, 0]})]
         shp, out = (128, 12, 12), (64, 6, 6)
-    elif case in ("dense_block", "dense_block_copy"):
+    elif case == "transition_wide":
+        # Cout = 128: the TMA transition kernel (2x2 pool commuted in front of the conv, four planes per stage)
+        inits = {**_bn(rng, 256, "bn"), "w": k(128, 256, 1, 1)}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1),
+                 onnx_lite.Node("AveragePool", ["c"], ["y"], {"kernel_shape": [2, 2], "strides": [2, 2], "pads": [0, 0, 0, 0]})]
+        shp, out = (256, 14, 14), (128, 7, 7)
+    elif case in ("dense_block", "dense_block_copy", "dense_block7"):
         # "dense_block": the first member is produced by a kernel -> in-place concat (channel slices);
         # "dense_block_copy": the first member is the graph input itself -> copy_channels fallback
         inits, nodes = {}, []
-        if case == "dense_block":
+        if case != "dense_block_copy":
             nodes.append(onnx_lite.Node("Relu", ["x"], ["x0"]))
             feats = ["x0"]
         else:
             feats = ["x"]
-        c = 64
-        for li in range(3):
+        c0 = c = 160 if case == "dense_block7" else 64      # dense_block7: 7x7 images, K tails, 4 layers in one kernel
+        hw = 7 if case == "dense_block7" else 9
+        for li in range(4 if case == "dense_block7" else 3):
             cat = f"cat{li}"
             nodes.append(onnx_lite.Node("Concat", list(feats), [cat], {"axis": 1}))
             inits.update(_bn(rng, c, f"bn{li}"))
@@ -122,7 +136,7 @@ def _build_case(case, tmp_path, rng):
             feats.append(f"f{li}")
             c += 32
         nodes.append(onnx_lite.Node("Concat", list(feats), ["y"], {"axis": 1}))
-        shp, out = (64, 9, 9), (160, 9, 9)
+        shp, out = (c0, hw, hw), (c, hw, hw)
     elif case == "cout256":
         inits = {"w": k(256, 128, 1, 1)}
         nodes = [_conv_node("x", "w", "y", 1)]
