@@ -17,8 +17,8 @@
 // Weights: bf16 [64][256], k = r*32 + (s+1)*4 + c (tap s sits at pixel s+1 of the 8-pixel window), TMA-loaded once
 // (SWIZZLE_128B) and resident for the lifetime of the CTA.
 //
-// Warp roles (448 threads): warps 0-7 input producers, 8-11 epilogue (tcgen05.ld -> bias/ReLU -> bf16/e4m3 ->
-// NHWC stores), 12 weight TMA, 13 MMA issuer.  Two input buffers (load of strip k+1 overlaps the MMAs of strip k)
+// Warp roles (448 threads): warps 0-3 input producers, 4-11 epilogue (two per TMEM lane quarter, 32 channels each:
+// tcgen05.ld -> packed scale/bias -> cvt(.relu) -> NHWC stores), 12 weight TMA, 13 MMA issuer.  Two input buffers (load of strip k+1 overlaps the MMAs of strip k)
 // and four TMEM accumulators of 64 columns.
 #include "kernels.h"
 #include "umma_ptx.cuh"
@@ -31,6 +31,7 @@ namespace {
 constexpr int kStemN = 64;                                  // MMA N (Cout padded to 64)
 constexpr int kStemWChunks = 4;                             // 7 x 32 bf16 = 448 B of K -> 4 chunks of 128 B
 constexpr int kStemWBytes = kStemWChunks * kStemN * 128;    // 32 KB resident weights
+constexpr int kStemProducers = 128;                         // warps 0-3 fill the input planes, warps 4-11 drain accumulators
 constexpr int kStemAcc = 4;                                 // TMEM accumulators (64 columns each)
 constexpr int kStemSlack = 2304;                            // junk slots of the last tile may read this far past a buffer
 constexpr int kStemMaxSmem = 227 * 1024;
@@ -76,12 +77,12 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
     if (warp == 12 && lane == 0) {
         MbarInit(w_bar, 1);
         for (int b = 0; b < 2; ++b) {
-            MbarInit(&in_full[b], 256);
+            MbarInit(&in_full[b], kStemProducers);
             MbarInit(&in_empty[b], 1);
         }
         for (int a = 0; a < kStemAcc; ++a) {
             MbarInit(&tmem_full[a], 1);
-            MbarInit(&tmem_empty[a], 128);
+            MbarInit(&tmem_empty[a], 8);  // one arrive per epilogue warp
         }
         FenceBarrierInit();
         PrefetchTensorMap(&tmap_w);
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
     GridDepLaunch();
     if (warp < 12) GridDepWait();
 
-    if (warp < 8) {
+    if (warp < 4) {
         // =========================================================== input producers: fp32 NCHW -> bf16 (c0,c1,c2,0) pixels
         const int tid = threadIdx.x;
         const int groups = p.W >> 2;  // 4-pixel groups per row
@@ -115,12 +116,12 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
             const int iy_base = 2 * sy * p.T - 3;
             const float* src = p.in + (size_t)img * p.Cin * plane;
             const uint32_t b0 = SmemAddr(s_buf + buf * p.buf_bytes);
-            for (int t0 = tid; t0 < tasks; t0 += 4 * 256) {
+            for (int t0 = tid; t0 < tasks; t0 += 4 * kStemProducers) {
                 float4 c[4][3];
                 uint32_t dst[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int t = t0 + u * 256;
+                    const int t = t0 + u * kStemProducers;
                     const int li = t / groups, g = t - li * groups;
                     const int iy = iy_base + li;
                     const bool ok = t < tasks && iy >= 0 && iy < p.H;
@@ -146,8 +147,10 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
         }
     } else if (warp < 12) {
         // =========================================================== epilogue
-        const int e = warp & 3;
+        // eight warps: TMEM lane quarter e = warp & 3, column half = (warp - 4) >> 2 (32 of the 64 channels each)
+        const int e = warp & 3, half = (warp - 4) >> 2;
         OutT* out = reinterpret_cast<OutT*>(p.out);
+        const uint32_t sc_addr = SmemAddr(s_out_scale) + half * 128, bi_addr = SmemAddr(s_bias) + half * 128;
         uint32_t tk = 0;
         for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
             const int img = strip / p.strips_per_img, sy = strip - img * p.strips_per_img;
@@ -157,45 +160,26 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
                 const int row = s / p.spr, ox = s - row * p.spr;
                 const int oy = sy * p.T + row;
                 const bool valid = row < p.T && ox < p.Wo && oy < p.Ho;
-                OutT* orow = out + ((size_t)(img * p.Ho + oy) * p.Wo + ox) * p.out_pitch + p.out_coff;
+                OutT* orow = out + ((size_t)(img * p.Ho + oy) * p.Wo + ox) * p.out_pitch + p.out_coff + half * 32;
                 MbarWait(&tmem_full[acc], aph);
                 TcFenceAfter();
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[32];
-                    TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kStemN + half * 32, r);
-                    TmemLoadWait();
-                    if (half == 1) {  // the accumulator is in registers: hand it back before the stores
-                        TcFenceBefore();
-                        MbarArrive(&tmem_empty[acc]);
-                    }
-                    if (valid) {
-                        float f[32];
-    #pragma unroll
-                        for (int q = 0; q < 32; q += 4) {
-                            float4 s4 = *reinterpret_cast<const float4*>(s_out_scale + half * 32 + q);
-                            float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * 32 + q);
-                            f[q] = fmaf(__uint_as_float(r[q]), s4.x, b4.x);
-                            f[q + 1] = fmaf(__uint_as_float(r[q + 1]), s4.y, b4.y);
-                            f[q + 2] = fmaf(__uint_as_float(r[q + 2]), s4.z, b4.z);
-                            f[q + 3] = fmaf(__uint_as_float(r[q + 3]), s4.w, b4.w);
-                        }
-                        if (p.post_relu) {
-    #pragma unroll
-                            for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], 0.f);
-                        }
-                        if (sizeof(OutT) == 2) {
-    #pragma unroll
-                            for (int q = 0; q < 32; q += 8)
-                                if (half * 32 + q < p.Cout) *reinterpret_cast<uint4*>(orow + half * 32 + q) = MmaElem<__nv_bfloat16>::Pack(f + q);
-                        } else {
-    #pragma unroll
-                            for (int q = 0; q < 32; q += 16)
-                                if (half * 32 + q < p.Cout) *reinterpret_cast<uint4*>(orow + half * 32 + q) = MmaElem<__nv_fp8_e4m3>::Pack(f + q);
-                        }
-                    }
-                    __syncwarp();
+                uint32_t r[32];
+                TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kStemN + half * 32, r);
+                TmemLoadWait();
+                TcFenceBefore();  // the accumulator slice is in registers: hand it back before the math and the stores
+                __syncwarp();
+                if (lane == 0) MbarArrive(&tmem_empty[acc]);
+                if (valid) {
+                    constexpr int kWords = 32 * (int)sizeof(OutT) / 4;
+                    uint32_t w[kWords];
+                    if (p.post_relu) EpiloguePack32Smem<OutT, true>(r, sc_addr, bi_addr, w);
+                    else EpiloguePack32Smem<OutT, false>(r, sc_addr, bi_addr, w);
+                    constexpr int kPer = 16 / (int)sizeof(OutT);  // channels per 16-byte store
+#pragma unroll
+                    for (int q = 0; q < kWords / 4; ++q)
+                        if (half * 32 + q * kPer < p.Cout) *reinterpret_cast<uint4*>(orow + q * kPer) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 12) {
