@@ -272,6 +272,21 @@ def main():
     e2e_value = B * e2e_steps * n_gpus / e2e_s if not in_process_multi else B * e2e_steps / e2e_s
     e2e_rel = float(np.abs(out - logits).max() / np.abs(logits).max())
 
+    # ---------------- same call with raw uint8 HWC pixels (the section-8f ingestion extension: 4x fewer PCIe bytes) ----------------
+    u8 = np.concatenate([synth.synthetic_images_u8(min(B, 32), start=rank * 32)] * ((B + 31) // 32))[:B]
+    u8_pinned_t = torch.from_numpy(np.ascontiguousarray(u8)).pin_memory()
+    inp_u8 = pkg.TensorData("data_0", u8_pinned_t.numpy(), pkg.DataType.UINT8)
+    for _ in range(2):
+        out_u8 = model.infer([inp_u8], outc)[0].data
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out_u8 = model.infer([inp_u8], outc)[0].data
+    u8_s = reduce_max(time.perf_counter() - t0)
+    barrier()
+    u8_value = B * e2e_steps * n_gpus / u8_s if not in_process_multi else B * e2e_steps / u8_s
+    u8_equal = bool(np.array_equal(out_u8, out))
+
     line = None
     if rank == 0:
         # ---------------- roofline of the dominant kernel family (per-step device events) ----------------
@@ -329,6 +344,9 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(B * 1000 * 4),
                         "steps": e2e_steps, "api": "ModelInfer (C-ABI) with pinned host buffers", "max_rel_vs_device_leg": e2e_rel},
+                "e2e_uint8": {"value": u8_value, "unit": UNIT, "h2d_bytes_per_step": int(u8.nbytes), "d2h_bytes_per_step": int(B * 1000 * 4),
+                              "steps": e2e_steps, "api": "ModelInfer with DATATYPE_UINT8 [N,H,W,3] pixels (extension; value/255 + layout on the GPU)",
+                              "logits_identical_to_float_path": u8_equal},
                 "roofline": roofline, "cpu_baseline": cpu, "latency": lat,
                 "wall_clock_check_ms_per_step": 1e3 * t_wall / args.steps}
     mgr.shutdown()

@@ -320,9 +320,21 @@ kernels::View Replica::MakeView(int tensor) const {
     return v;
 }
 
-void Replica::EnqueueStep(size_t i, int n, int off) {
+const uint8_t* Replica::U8Source(int tensor, int off, unsigned u8_mask) {
+    if (!u8_mask || tensor < 0) return nullptr;
+    const TensorDesc& t = plan_->tensors[tensor];
+    const BufferDesc& b = plan_->buffers[t.buffer];
+    if (b.role != BufferDesc::Role::Input || b.io_index < 0 || !((u8_mask >> b.io_index) & 1u)) return nullptr;
+    if ((size_t)b.io_index >= u8_stage_.size() || !u8_stage_[b.io_index]) throw CudaError("uint8 input was not staged");
+    return u8_stage_[b.io_index] + (size_t)off * t.C * t.H * t.W;
+}
+
+void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
     const Step& s = plan_->steps[i];
     const Prepared& pr0 = prepared_[i];
+    const uint8_t* u8 = U8Source(s.in, off, u8_mask);
+    if (u8 && !(s.kind == StepKind::NchwToNhwc || (s.kind == StepKind::Conv && s.stem_nchw && pr0.use_umma)))
+        throw CudaError("step '" + s.name + "' cannot ingest a uint8 input (only image inputs feeding the layout pass or the stem can)");
     // views of graph inputs/outputs are indexed by the sub-batch offset; everything else is scratch
     kernels::View vin = pr0.in, vin2 = pr0.in2, vout = pr0.out;
     if (off) {
@@ -332,13 +344,16 @@ void Replica::EnqueueStep(size_t i, int n, int off) {
     }
     cudaError_t e = cudaSuccess;
     switch (s.kind) {
-        case StepKind::NchwToNhwc: e = kernels::NchwToNhwc((const float*)vin.base, vout, n, stream_); break;
+        case StepKind::NchwToNhwc:
+            e = u8 ? kernels::U8HwcToNhwc(u8, vout, n, stream_) : kernels::NchwToNhwc((const float*)vin.base, vout, n, stream_);
+            break;
         case StepKind::NhwcToNchw: e = kernels::NhwcToNchw(vin, (float*)vout.base, n, stream_); break;
         case StepKind::Conv: {
             kernels::ConvArgs a = pr0.conv;
             a.in = vin;
             a.out = vout;
             a.n = n;
+            a.in_u8_hwc = u8;
             e = pr0.use_umma ? kernels::ConvUmma(a, pr0.umma, stream_) : kernels::ConvSimtF32(a, pr0.w_kn, stream_);
             break;
         }
@@ -356,10 +371,10 @@ void Replica::EnqueueStep(size_t i, int n, int off) {
     if (e != cudaSuccess) CudaCheck(e, ("step '" + s.name + "' (" + StepKindName(s.kind) + ")").c_str());
 }
 
-size_t Replica::EnqueueAt(size_t i, int n, int off) {
+size_t Replica::EnqueueAt(size_t i, int n, int off, unsigned u8_mask) {
     const int r = prepared_[i].fused_run;
     if (r < 0) {
-        EnqueueStep(i, n, off);
+        EnqueueStep(i, n, off, u8_mask);
         return 1;
     }
     DenseRun& run = dense_runs_[r];
@@ -370,20 +385,20 @@ size_t Replica::EnqueueAt(size_t i, int n, int off) {
     return (size_t)run.num_layers * 2;
 }
 
-void Replica::Enqueue(int n, int off) {
+void Replica::Enqueue(int n, int off, unsigned u8_mask) {
     if (n <= 0 || off < 0 || off + n > plan_->max_batch) throw CudaError("batch " + std::to_string(off + n) + " exceeds the planned maximum");
     if (!use_graphs_) {
-        for (size_t i = 0; i < plan_->steps.size();) i += EnqueueAt(i, n, off);
+        for (size_t i = 0; i < plan_->steps.size();) i += EnqueueAt(i, n, off, u8_mask);
         return;
     }
-    const int64_t key = ((int64_t)off << 20) | (int64_t)n;
+    const int64_t key = ((int64_t)(u8_mask & 0xFFu) << 44) | ((int64_t)off << 20) | (int64_t)n;
     auto it = graphs_.find(key);
     if (it == graphs_.end()) {
         cudaGraph_t graph = nullptr;
         uint64_t before = kernels::LaunchCount();
         CudaCheck(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
         try {
-            for (size_t i = 0; i < plan_->steps.size();) i += EnqueueAt(i, n, off);
+            for (size_t i = 0; i < plan_->steps.size();) i += EnqueueAt(i, n, off, u8_mask);
         } catch (...) {
             cudaStreamEndCapture(stream_, &graph);
             if (graph) cudaGraphDestroy(graph);
@@ -409,31 +424,47 @@ void Replica::Enqueue(int n, int off) {
 }
 
 void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
-                  const std::vector<size_t>& out_capacity_bytes) {
+                  const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask) {
     std::lock_guard<std::mutex> lk(mu_);
     DeviceGuard g(device_);
     const Plan& P = *plan_;
+    // destination and bytes per sample of every graph input (fp32 NCHW into the arena, or raw uint8 into its staging buffer)
+    if (u8_mask) u8_stage_.resize(P.inputs.size(), nullptr);
+    auto in_dst = [&](size_t i) -> char* {
+        const TensorDesc& t = P.tensors[P.inputs[i]];
+        if (!((u8_mask >> i) & 1u)) return (char*)BufferPtr(t.buffer);
+        if (!u8_stage_[i]) {
+            const size_t bytes = (size_t)P.max_batch * t.C * t.H * t.W + 256;
+            CudaCheck(cudaMalloc((void**)&u8_stage_[i], bytes), "cudaMalloc(uint8 staging)");
+            allocations_.push_back(u8_stage_[i]);
+            device_bytes_ += bytes;
+        }
+        return (char*)u8_stage_[i];
+    };
+    auto in_stride = [&](size_t i) -> size_t {
+        const TensorDesc& t = P.tensors[P.inputs[i]];
+        return (size_t)t.C * t.H * t.W * (((u8_mask >> i) & 1u) ? 1 : 4);
+    };
     // Large batches are pipelined in sub-batches: the H2D copy of sub-batch k+1 (copy stream) overlaps the forward
     // of sub-batch k (compute stream).  The fp32 NCHW input is 602 KB per image, so at bs256 the PCIe transfer is
     // as long as the whole forward; without overlap the two add up.
-    const int chunk = pipeline_chunk_ > 0 ? pipeline_chunk_ : n;
+    // uint8 pixels are 4x smaller than the fp32 tensor: their H2D (0.75 ms per 256 images) is cheaper than the efficiency two
+    // half-size forwards lose, so they are not split (measured: 3.05 ms unsplit vs 3.64 ms in two pieces)
+    static const bool chunk_forced = getenv("B200_ENGINE_PIPELINE_CHUNK") != nullptr;
+    const int chunk = (u8_mask && !chunk_forced) ? n : (pipeline_chunk_ > 0 ? pipeline_chunk_ : n);
     const int pieces = std::min<int>((n + chunk - 1) / chunk, (int)copy_events_.size());
     if (pieces <= 1) {
-        for (size_t i = 0; i < P.inputs.size(); ++i) {
-            const TensorDesc& t = P.tensors[P.inputs[i]];
-            size_t bytes = (size_t)n * t.C * t.H * t.W * 4;
-            CudaCheck(cudaMemcpyAsync(BufferPtr(t.buffer), host_inputs[i], bytes, cudaMemcpyHostToDevice, stream_), "H2D input");
-        }
-        Enqueue(n);
+        for (size_t i = 0; i < P.inputs.size(); ++i)
+            CudaCheck(cudaMemcpyAsync(in_dst(i), host_inputs[i], (size_t)n * in_stride(i), cudaMemcpyHostToDevice, stream_), "H2D input");
+        Enqueue(n, 0, u8_mask);
     } else {
         const int per = (n + pieces - 1) / pieces;
         for (int k = 0; k < pieces; ++k) {
             const int off = k * per, cnt = std::min(per, n - off);
             if (cnt <= 0) break;
             for (size_t i = 0; i < P.inputs.size(); ++i) {
-                const TensorDesc& t = P.tensors[P.inputs[i]];
-                const size_t stride = (size_t)t.C * t.H * t.W * 4;
-                CudaCheck(cudaMemcpyAsync((char*)BufferPtr(t.buffer) + off * stride, (const char*)host_inputs[i] + off * stride,
+                const size_t stride = in_stride(i);
+                CudaCheck(cudaMemcpyAsync(in_dst(i) + off * stride, (const char*)host_inputs[i] + off * stride,
                                           cnt * stride, cudaMemcpyHostToDevice, copy_stream_), "H2D input (pipelined)");
             }
             CudaCheck(cudaEventRecord(copy_events_[k], copy_stream_), "event record");
@@ -442,7 +473,7 @@ void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std:
             const int off = k * per, cnt = std::min(per, n - off);
             if (cnt <= 0) break;
             CudaCheck(cudaStreamWaitEvent(stream_, copy_events_[k], 0), "stream wait event");
-            Enqueue(cnt, off);
+            Enqueue(cnt, off, u8_mask);
         }
     }
     for (size_t i = 0; i < P.outputs.size() && i < host_outputs.size(); ++i) {

@@ -34,8 +34,10 @@ public:
 
     // Host-to-host forward of `n` samples (n <= plan.max_batch): H2D of every graph input, all steps,
     // D2H of every graph output (min(capacity, produced) bytes each).  Blocking.  Thread-safe (serialised).
+    // `u8_mask` bit i: graph input i is raw uint8 [n][H][W][C] pixels (value / 255 is applied on the GPU) instead of the
+    // graph's fp32 NCHW tensor - the uint8-ingestion extension of SURVEY.md section 8f.
     void Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
-             const std::vector<size_t>& out_capacity_bytes);
+             const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask = 0);
 
     // Measurement helpers (extension API).
     void StageInput(int input_index, const void* host, int n);
@@ -67,9 +69,10 @@ private:
 
     // Every step on stream_ for samples [off, off+n) of the staged batch (captured into a graph when enabled).
     // Only graph-input / graph-output buffers are indexed by `off`; all intermediate buffers are reused.
-    void Enqueue(int n, int off = 0);
-    void EnqueueStep(size_t i, int n, int off = 0);
-    size_t EnqueueAt(size_t i, int n, int off);  // runs step i (or the fused run starting there); returns steps consumed
+    void Enqueue(int n, int off = 0, unsigned u8_mask = 0);
+    void EnqueueStep(size_t i, int n, int off = 0, unsigned u8_mask = 0);
+    size_t EnqueueAt(size_t i, int n, int off, unsigned u8_mask = 0);
+    const uint8_t* U8Source(int tensor, int off, unsigned u8_mask);  // device uint8 staging of a graph input, or null  // runs step i (or the fused run starting there); returns steps consumed
     void BuildDenseRuns();
     kernels::View MakeView(int tensor) const;
     void* BufferPtr(int buffer) const;
@@ -90,6 +93,7 @@ private:
     std::vector<const float*> dconst_;  // fp32 device copy of every Plan::consts entry that is used as a vector
     std::vector<Prepared> prepared_;
     std::vector<DenseRun> dense_runs_;
+    std::vector<uint8_t*> u8_stage_;  // per graph input: device staging for uint8 ingestion (allocated on first use)
     std::map<int64_t, cudaGraphExec_t> graphs_;  // key: (off << 20) | n
     std::map<int64_t, int> graph_launches_;  // kernels per captured forward, for the launch counter
     int launches_per_forward_ = 0;

@@ -35,6 +35,7 @@ struct ConvArgs {
     bool post_relu = false;
     bool pool2 = false;  // A rows are 2x2 averages of (prologue-transformed) input pixels
     bool stem_nchw = false;  // `in` is the caller's fp32 NCHW image batch (7x7/s2/p3 stem, see kernels_stem.cu)
+    const uint8_t* in_u8_hwc = nullptr;  // stem_nchw only: read raw uint8 [n][H][W][C] pixels instead (value / 255)
 };
 
 // A CUtensorMap by value (128 bytes, 64-byte aligned) without pulling <cuda.h> into every translation unit.
@@ -98,6 +99,8 @@ cudaError_t DenseBlockFp8(const DenseBlockArgs& a, cudaStream_t stream);
 
 // ---- memory-bound kernels (templated on element type inside) ----
 cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);
+// uint8 ingestion: raw [n][H][W][C] uint8 pixels -> value / 255 in the internal NHWC layout
+cudaError_t U8HwcToNhwc(const uint8_t* in, View out, int n, cudaStream_t stream);
 cudaError_t NhwcToNchw(View in, float* out, int n, cudaStream_t stream);
 cudaError_t MaxPool(View in, View out, int n, int k, int stride, int pad, cudaStream_t stream);
 cudaError_t AvgPool(View in, View out, int n, int k, int stride, int pad, bool count_include_pad, cudaStream_t stream);

@@ -98,6 +98,17 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, DView out, int
 }
 
 template <typename T>
+__global__ void u8hwc_to_nhwc_kernel(const uint8_t* __restrict__ in, DView out, int n) {
+    size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (size_t)n * out.H * out.W) return;
+    T* o = reinterpret_cast<T*>(out.base) + pix * out.pitch + out.c_off;
+    const uint8_t* s = in + pix * out.C;
+    for (int c = 0; c < out.C; ++c) Elem<T>::st(o + c, (float)s[c] / 255.0f);  // same arithmetic as client/test_client.py: img / 255
+    if (out.c_off == 0)
+        for (int c = out.C; c < out.pitch; ++c) Elem<T>::st(o + c, 0.f);
+}
+
+template <typename T>
 __global__ void nhwc_to_nchw_kernel(DView in, float* __restrict__ out, int n) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t hw = (size_t)in.H * in.W;
@@ -609,6 +620,14 @@ cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream) {
     size_t pixels = (size_t)n * out.H * out.W;
     if (!pixels) return cudaSuccess;
     DISPATCH_DTYPE(out.dtype, (nchw_to_nhwc_kernel<T><<<Blocks(pixels, 256), 256, 0, stream>>>(in, ToD(out), n)));
+    CountLaunch();
+    return cudaGetLastError();
+}
+
+cudaError_t U8HwcToNhwc(const uint8_t* in, View out, int n, cudaStream_t stream) {
+    size_t pixels = (size_t)n * out.H * out.W;
+    if (!pixels) return cudaSuccess;
+    DISPATCH_DTYPE(out.dtype, (u8hwc_to_nhwc_kernel<T><<<Blocks(pixels, 256), 256, 0, stream>>>(in, ToD(out), n)));
     CountLaunch();
     return cudaGetLastError();
 }

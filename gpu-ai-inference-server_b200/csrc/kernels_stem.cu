@@ -37,6 +37,7 @@ constexpr int kStemSlack = 2304;                            // junk slots of the
 constexpr int kStemMaxSmem = 227 * 1024;
 
 struct SParams {
+    const uint8_t* in_u8;  // raw [n][H][W][Cin] uint8 pixels (value / 255) when non-null, else:
     const float* in;  // [n][Cin][H][W] fp32
     void* out;        // NHWC
     const float* out_scale;
@@ -127,9 +128,34 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
                     const bool ok = t < tasks && iy >= 0 && iy < p.H;
                     const float* q = src + (size_t)(ok ? iy : 0) * p.W + 4 * g;
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        c[u][ch] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok && ch < p.Cin) c[u][ch] = __ldg(reinterpret_cast<const float4*>(q + ch * plane));
+                    for (int ch = 0; ch < 3; ++ch) c[u][ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.in_u8) {
+                        // uint8 ingestion: four HWC pixels = 4*Cin consecutive bytes; value / 255 exactly as the reference client
+                        if (ok) {
+                            const uint8_t* b = p.in_u8 + (((size_t)img * p.H + iy) * p.W + 4 * g) * p.Cin;
+                            float v[4][3];
+                            if (p.Cin == 3) {
+                                const uint32_t* w = reinterpret_cast<const uint32_t*>(b);  // 12 bytes, 4-byte aligned (W % 4 == 0)
+                                const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                                const uint32_t by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u,
+                                                         (w1 >> 16) & 255u, w1 >> 24, w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+#pragma unroll
+                                for (int px = 0; px < 4; ++px)
+#pragma unroll
+                                    for (int ch = 0; ch < 3; ++ch) v[px][ch] = (float)by[3 * px + ch] / 255.0f;
+                            } else {
+#pragma unroll
+                                for (int px = 0; px < 4; ++px)
+#pragma unroll
+                                    for (int ch = 0; ch < 3; ++ch) v[px][ch] = ch < p.Cin ? (float)b[px * p.Cin + ch] / 255.0f : 0.f;
+                            }
+#pragma unroll
+                            for (int ch = 0; ch < 3; ++ch) c[u][ch] = make_float4(v[0][ch], v[1][ch], v[2][ch], v[3][ch]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch)
+                            if (ok && ch < p.Cin) c[u][ch] = __ldg(reinterpret_cast<const float4*>(q + ch * plane));
                     }
                     dst[u] = t < tasks ? b0 + (uint32_t)((li & 1) * p.plane1_off + (li >> 1) * p.row_pitch + 32 + 32 * g) : 0u;
                 }
@@ -279,12 +305,13 @@ cudaError_t LaunchStem(const CUtensorMap& tm, const SParams& p, cudaStream_t str
 
 bool StemNchwSupported(const ConvArgs& a) {
     if (!a.stem_nchw) return false;
-    if (a.in.dtype != DType::F32 || (a.out.dtype != DType::BF16 && a.out.dtype != DType::FP8)) return false;
+    if ((!a.in_u8_hwc && a.in.dtype != DType::F32) || (a.out.dtype != DType::BF16 && a.out.dtype != DType::FP8)) return false;
     if (!StemFusable(a.Cin, a.Cout, a.R, a.S, a.stride, a.pad, a.in.H, a.in.W)) return false;
     if (a.pre_scale || a.pool2) return false;
     const int esz = (int)DTypeSize(a.out.dtype);
     if ((a.out.pitch * esz) % 16 != 0 || (a.out.c_off * esz) % 16 != 0) return false;
-    if (reinterpret_cast<uintptr_t>(a.in.base) % 16 != 0) return false;
+    if (!a.in_u8_hwc && reinterpret_cast<uintptr_t>(a.in.base) % 16 != 0) return false;
+    if (a.in_u8_hwc && reinterpret_cast<uintptr_t>(a.in_u8_hwc) % 4 != 0) return false;
     SParams p;
     return StemGeometry(a.in.H, a.in.W, &p);
 }
@@ -296,6 +323,7 @@ cudaError_t ConvStemNchw(const ConvArgs& a, const UmmaWeights& w, cudaStream_t s
     if (!StemGeometry(a.in.H, a.in.W, &p)) return cudaErrorInvalidValue;
     if (p.Ho != a.out.H || p.Wo != a.out.W) return cudaErrorInvalidValue;
     p.in = reinterpret_cast<const float*>(a.in.base);
+    p.in_u8 = a.in_u8_hwc;
     p.out = a.out.base;
     p.out_scale = w.out_scale;
     p.bias = a.bias;

@@ -344,11 +344,22 @@ bool ModelImpl::ValidateInputs(const std::vector<IoDesc>& ins) const {
             return false;
         }
         auto ti = config_.input_types.find(in.name);
+        auto si = config_.input_shapes.find(in.name);
+        // Extension: an image input declared FLOAT32 [N,C,H,W] with C <= 4 also accepts the raw
+        // UINT8 [N,H,W,C] pixels; the GPU applies value / 255 and the layout change (client/test_client.py:186-194).
+        if (in.dtype == DataType::UINT8 && ti != config_.input_types.end() && ti->second == DataType::FLOAT32 &&
+            si != config_.input_shapes.end() && si->second.dims.size() == 4 && in.dims.size() == 4) {
+            const auto& want = si->second.dims;
+            if (want[1] >= 1 && want[1] <= 4 && in.dims[3] == want[1] && (want[2] == -1 || in.dims[1] == want[2]) &&
+                (want[3] == -1 || in.dims[2] == want[3]) && (want[0] == -1 || want[0] == in.dims[0]))
+                continue;
+            SetLastError("Input shape mismatch for " + in.name + ": a UINT8 image must be [N,H,W,C]");
+            return false;
+        }
         if (ti != config_.input_types.end() && ti->second != in.dtype) {
             SetLastError("Input data type mismatch for " + in.name);
             return false;
         }
-        auto si = config_.input_shapes.find(in.name);
         if (si != config_.input_shapes.end()) {
             const auto& want = si->second.dims;
             if (want.size() != in.dims.size()) {
@@ -414,13 +425,25 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
         const b200::Plan& P = *st->plan;
         // by-name binding of graph inputs (reference model.cpp:1173-1222)
         std::vector<const void*> ptrs(P.input_names.size(), nullptr);
+        unsigned u8_mask = 0;
         int64_t n = -1;
         for (size_t gi = 0; gi < P.input_names.size(); ++gi) {
             const IoDesc* found = nullptr;
             for (const auto& in : ins) if (in.name == P.input_names[gi]) { found = &in; break; }
             if (!found) throw std::runtime_error("Required input tensor not provided: " + P.input_names[gi]);
-            if (found->dtype != DataType::FLOAT32) throw std::runtime_error("Unsupported data type for input: " + found->name);
             const auto& gd = P.input_dims[gi];
+            if (found->dtype == DataType::UINT8 && gd.size() == 4 && found->dims.size() == 4 && gi < 8) {
+                // raw [N,H,W,C] pixels for a [N,C,H,W] graph input
+                if (found->dims[0] < 1 || found->dims[1] != gd[2] || found->dims[2] != gd[3] || found->dims[3] != gd[1])
+                    throw std::runtime_error("Input shape mismatch for " + found->name + ": a UINT8 image must be [N,H,W,C]");
+                if (n < 0) n = found->dims[0];
+                else if (n != found->dims[0]) throw std::runtime_error("Inputs disagree on the batch dimension");
+                if (!found->data || found->bytes < (size_t)n * gd[1] * gd[2] * gd[3]) throw std::runtime_error("Invalid UINT8 data for input: " + found->name);
+                ptrs[gi] = found->data;
+                u8_mask |= 1u << gi;
+                continue;
+            }
+            if (found->dtype != DataType::FLOAT32) throw std::runtime_error("Unsupported data type for input: " + found->name);
             if (found->dims.size() != gd.size() || found->dims.empty() || found->dims[0] < 1)
                 throw std::runtime_error("Invalid FLOAT32 data for input: " + found->name);
             size_t per = 1;
@@ -433,7 +456,7 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
             if (!found->data || found->bytes < (size_t)n * per * 4) throw std::runtime_error("Invalid FLOAT32 data for input: " + found->name);
             ptrs[gi] = found->data;
         }
-        ok = Execute(*st, (int)n, ptrs, outs);
+        ok = Execute(*st, (int)n, ptrs, outs, u8_mask);
     } catch (const std::exception& e) {
         SetLastError(std::string("ONNX inference error: ") + e.what());
         ok = false;
@@ -471,14 +494,14 @@ std::vector<ShardPlan> PlanShards(int n, int G, int max_batch, int min_shard, in
 
 // The multi-GPU batch scheduler: contiguous split of the batch over replicas, no collective
 // (SURVEY.md §8e).  Small batches go to one replica chosen round-robin so concurrent callers spread.
-bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs) {
+bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs, unsigned u8_mask) {
     const b200::Plan& P = *st.plan;
     const int G = (int)st.replicas.size();
     const int max_b = P.max_batch;
     std::vector<size_t> in_stride(P.inputs.size()), out_stride(P.outputs.size());
     for (size_t i = 0; i < P.inputs.size(); ++i) {
         const auto& t = P.tensors[P.inputs[i]];
-        in_stride[i] = (size_t)t.C * t.H * t.W * 4;
+        in_stride[i] = (size_t)t.C * t.H * t.W * (((u8_mask >> i) & 1u) ? 1 : 4);
     }
     for (size_t i = 0; i < P.outputs.size(); ++i) {
         const auto& t = P.tensors[P.outputs[i]];
@@ -512,7 +535,7 @@ bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_pt
             op[i] = (char*)outs[i].data + begin;
             cap[i] = outs[i].capacity - begin;
         }
-        st.replicas[s.replica]->Run(s.cnt, ip, op, cap);
+        st.replicas[s.replica]->Run(s.cnt, ip, op, cap, u8_mask);
     };
     if (single) {
         for (auto& s : shards) run_shard(s);

@@ -64,7 +64,7 @@ public:
 
 private:
     bool ValidateInputs(const std::vector<IoDesc>& ins) const;
-    bool Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs);
+    bool Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs, unsigned u8_mask = 0);
 
     std::string model_path_;
     ModelType type_;

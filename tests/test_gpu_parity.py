@@ -215,6 +215,29 @@ def test_densenet_low_precision_top5_agreement(pkg, repo_dir, densenet_path, mon
     assert a["max_rel"] < (0.05 if precision == "bf16" else 0.3), a
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp8"])
+def test_uint8_hwc_ingestion_matches_the_float_path(pkg, repo_dir, monkeypatch, precision):
+    """raw uint8 [N,H,W,C] pixels through the same ModelInfer entry point; the GPU applies the
+    client's `img / 255` and the HWC->CHW change (client/test_client.py:186-194).  Same arithmetic => identical logits."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", precision)
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "8")
+    monkeypatch.setenv("B200_ENGINE_PIPELINE_CHUNK", "3")
+    u8 = synth.synthetic_images_u8(7, start=6000)                    # [N,H,W,3] uint8
+    x = synth.to_model_input(u8)                                     # [N,3,H,W] float32 = u8 / 255
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        ref = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [7, 1000])])[0].data.copy()
+        got = m.infer([pkg.TensorData("data_0", np.ascontiguousarray(u8), pkg.DataType.UINT8)], [pkg.OutputConfig("fc6_1", [7, 1000])])[0].data
+        assert np.isfinite(got).all()
+        assert np.array_equal(got, ref), float(np.abs(got - ref).max())
+        with pytest.raises(pkg.EngineError, match="a UINT8 image must be \\[N,H,W,C\\]"):
+            m.infer([pkg.TensorData("data_0", np.zeros((1, 3, 224, 224), np.uint8), pkg.DataType.UINT8)], [pkg.OutputConfig("fc6_1", [1, 1000])])
+    finally:
+        mgr.shutdown()
+
+
 def test_batch_properties_and_chunking(pkg, repo_dir, monkeypatch):
     """Size-independent properties: per-image results do not depend on batch composition, batch order,
     or on how the batch is chunked through the arena (max_batch 4 < n)."""
