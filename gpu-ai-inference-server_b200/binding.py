@@ -106,7 +106,7 @@ EXPORTED_SYMBOLS = [
 ]
 EXTENSION_SYMBOLS = [
     "B200EngineVersion", "B200PlanDescribe", "B200PlanShards", "B200KernelLaunchCount", "B200ModelStageInput", "B200ModelForwardDevice",
-    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue",
+    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats",
 ]
 
 
@@ -147,6 +147,7 @@ def load_library() -> C.CDLL:
         "B200ModelReadOutput": (b, [vp, C.POINTER(C.c_float), sz, err]),
         "B200ModelProfileSteps": (vp, [vp, i, i, err]),
         "B200ModelReadValue": (C.c_int64, [vp, cp, C.POINTER(C.c_float), sz, err]),
+        "B200ModelCoalesceStats": (b, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == missing export
@@ -378,6 +379,12 @@ class Model:
         return st
 
     # ---- extension API (include/b200_engine.h) ----
+    def coalesce_stats(self):
+        """(batches executed by the request coalescer, requests they carried)"""
+        nb, nr = C.c_int64(0), C.c_int64(0)
+        load_library().B200ModelCoalesceStats(self._h, C.byref(nb), C.byref(nr))
+        return int(nb.value), int(nr.value)
+
     def stage_input(self, t: TensorData) -> None:
         keep: list = []
         buf = np.ascontiguousarray(t.data, dtype=np.float32)

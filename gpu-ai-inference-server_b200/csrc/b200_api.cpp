@@ -150,4 +150,12 @@ int64_t B200ModelReadValue(ModelHandle handle, const char* value_name, float* ou
     }
 }
 
+
+bool B200ModelCoalesceStats(ModelHandle handle, int64_t* batches, int64_t* requests) {
+    std::shared_ptr<inference::Model> keep;
+    auto st = PinHandle(handle, &keep, nullptr);
+    if (!st || !batches || !requests) return false;
+    keep->Impl()->CoalesceStats(batches, requests);
+    return true;
+}
 }  // extern "C"

@@ -485,6 +485,52 @@ void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std:
     CudaCheck(cudaStreamSynchronize(stream_), "forward");
 }
 
+void Replica::RunSegments(const std::vector<Segment>& segs, unsigned u8_mask) {
+    std::lock_guard<std::mutex> lk(mu_);
+    DeviceGuard g(device_);
+    const Plan& P = *plan_;
+    int total = 0;
+    for (const auto& s : segs) total += s.n;
+    if (total <= 0) return;
+    if (total > P.max_batch) throw CudaError("coalesced batch exceeds the planned maximum");
+    if (u8_mask) u8_stage_.resize(P.inputs.size(), nullptr);
+    int off = 0;
+    for (const auto& s : segs) {
+        for (size_t i = 0; i < P.inputs.size(); ++i) {
+            const TensorDesc& t = P.tensors[P.inputs[i]];
+            const bool u8 = (u8_mask >> i) & 1u;
+            const size_t stride = (size_t)t.C * t.H * t.W * (u8 ? 1 : 4);
+            char* dst;
+            if (u8) {
+                if (!u8_stage_[i]) {
+                    const size_t bytes = (size_t)P.max_batch * t.C * t.H * t.W + 256;
+                    CudaCheck(cudaMalloc((void**)&u8_stage_[i], bytes), "cudaMalloc(uint8 staging)");
+                    allocations_.push_back(u8_stage_[i]);
+                    device_bytes_ += bytes;
+                }
+                dst = (char*)u8_stage_[i];
+            } else {
+                dst = (char*)BufferPtr(t.buffer);
+            }
+            CudaCheck(cudaMemcpyAsync(dst + (size_t)off * stride, s.in[i], (size_t)s.n * stride, cudaMemcpyHostToDevice, stream_), "H2D input (coalesced)");
+        }
+        off += s.n;
+    }
+    Enqueue(total, 0, u8_mask);
+    off = 0;
+    for (const auto& s : segs) {
+        for (size_t i = 0; i < P.outputs.size() && i < s.out.size(); ++i) {
+            const TensorDesc& t = P.tensors[P.outputs[i]];
+            const size_t stride = (size_t)t.C * t.H * t.W * 4;
+            const size_t bytes = std::min((size_t)s.n * stride, s.cap[i]);
+            if (s.out[i] && bytes)
+                CudaCheck(cudaMemcpyAsync(s.out[i], (char*)BufferPtr(t.buffer) + (size_t)off * stride, bytes, cudaMemcpyDeviceToHost, stream_), "D2H output (coalesced)");
+        }
+        off += s.n;
+    }
+    CudaCheck(cudaStreamSynchronize(stream_), "forward (coalesced)");
+}
+
 void Replica::StageInput(int input_index, const void* host, int n) {
     std::lock_guard<std::mutex> lk(mu_);
     DeviceGuard g(device_);

@@ -39,6 +39,17 @@ public:
     void Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
              const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask = 0);
 
+    // Several callers' requests as ONE batch (request coalescing): every segment's inputs are
+    // copied from its own host buffers to consecutive sample offsets, one forward of the total runs, and every segment's
+    // outputs go straight back to its own host buffers.  sum(n) <= plan.max_batch.
+    struct Segment {
+        int n = 0;
+        std::vector<const void*> in;   // per graph input
+        std::vector<void*> out;        // per graph output (may hold nulls)
+        std::vector<size_t> cap;       // bytes available at each out
+    };
+    void RunSegments(const std::vector<Segment>& segs, unsigned u8_mask = 0);
+
     // Measurement helpers (extension API).
     void StageInput(int input_index, const void* host, int n);
     float ForwardTimed(int n, bool flush_l2);  // ms between events on this replica's stream

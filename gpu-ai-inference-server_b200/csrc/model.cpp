@@ -256,9 +256,13 @@ bool ModelImpl::Load() {
                     b200::json::Value v = b200::json::ParseString(ss.str());
                     if (auto* p = v.Get("precision")) if (p->kind == b200::json::Value::String) precision_s = p->str;
                     if (auto* p = v.Get("max_batch_size")) if (p->kind == b200::json::Value::Number && p->num >= 1) max_batch = (int)p->num;
+                    if (auto* p = v.Get("dynamic_batching")) if (p->kind == b200::json::Value::Bool && p->b) config_.dynamic_batching = true;
                 } catch (...) { /* a malformed config.json never blocks loading (the reference ignores it) */ }
             }
         }
+        // request coalescing window: the reference's dead `dynamic_batching` flag switches it on (200 us), the environment wins
+        coalesce_us_ = atoi(EnvOr("B200_ENGINE_COALESCE_US", config_.dynamic_batching ? "200" : "0").c_str());
+        coalesce_small_ = std::max(1, atoi(EnvOr("B200_ENGINE_COALESCE_MAX_REQUEST", "8").c_str()));
         precision_s = EnvOr("B200_ENGINE_PRECISION", precision_s);
         max_batch = atoi(EnvOr("B200_ENGINE_MAX_BATCH", std::to_string(max_batch)).c_str());
         if (max_batch < 1) max_batch = 1;
@@ -456,7 +460,8 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
             if (!found->data || found->bytes < (size_t)n * per * 4) throw std::runtime_error("Invalid FLOAT32 data for input: " + found->name);
             ptrs[gi] = found->data;
         }
-        ok = Execute(*st, (int)n, ptrs, outs, u8_mask);
+        if (coalesce_us_ > 0 && n <= coalesce_small_ && n < P.max_batch) ok = Coalesce(st, (int)n, ptrs, outs, u8_mask);
+        else ok = Execute(*st, (int)n, ptrs, outs, u8_mask);
     } catch (const std::exception& e) {
         SetLastError(std::string("ONNX inference error: ") + e.what());
         ok = false;
@@ -467,6 +472,104 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
     total_ns_.fetch_add(ns);
     last_ns_.store(ns);
     return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Request coalescer.  gin serves every REST request on its own goroutine / OS thread and the reference's handler sends
+// batch 1, so concurrent callers arrive here one image at a time.  The first caller of a quiet period
+// becomes the leader: it waits up to `coalesce_us_` (or until the arena is full) while followers append their requests,
+// then runs everything that accumulated as ONE batch - each request's input is copied from its own buffer to its sample
+// offset, each result goes straight back to its own output buffer - and wakes the followers.  Requests left over when
+// the leader closes its batch elect (promote) their own leader immediately.
+bool ModelImpl::Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::vector<const void*>& ptrs, std::vector<OutDesc>& outs,
+                         unsigned u8_mask) {
+    Pending me;
+    me.n = n; me.u8_mask = u8_mask; me.ptrs = ptrs; me.outs = &outs;
+    const int cap = st->plan->max_batch;
+    std::unique_lock<std::mutex> lk(co_mu_);
+    co_queue_.push_back(&me);
+    bool lead = !co_leader_;
+    bool waited = false;
+    for (;;) {
+        if (!lead) {
+            co_cv_.notify_one();  // the leader re-checks whether its batch is full
+            me.cv.wait(lk, [&] { return me.done || me.promoted; });
+            if (me.done) {
+                if (!me.ok) SetLastError(me.err);
+                return me.ok;
+            }
+            lead = true;     // promoted: the requests that did not fit the previous batch already waited their window
+            waited = true;
+        }
+        co_leader_ = true;
+        auto queued = [&] { int s = 0; for (auto* p : co_queue_) s += p->n; return s; };
+        if (!waited) co_cv_.wait_for(lk, std::chrono::microseconds(coalesce_us_), [&] { return queued() >= cap; });
+        // close the batch: queue order, same input kind as the first request, total <= cap
+        std::vector<Pending*> batch, rest;
+        int total = 0;
+        for (auto* p : co_queue_) {
+            if (p->u8_mask == co_queue_.front()->u8_mask && total + p->n <= cap) { batch.push_back(p); total += p->n; }
+            else rest.push_back(p);
+        }
+        co_queue_.swap(rest);
+        co_leader_ = false;
+        const bool mine = std::find(batch.begin(), batch.end(), &me) != batch.end();
+        if (!co_queue_.empty()) {
+            // somebody else must lead what is left (possibly me, if my request did not fit)
+            Pending* next = mine ? co_queue_.front() : &me;
+            if (next != &me) { co_leader_ = true; next->promoted = true; next->cv.notify_one(); }
+        }
+        lk.unlock();
+        std::string err;
+        bool ok = true;
+        try {
+            RunCoalesced(*st, batch);
+        } catch (const std::exception& e) {
+            ok = false;
+            err = std::string("ONNX inference error: ") + e.what();
+        }
+        co_batches_.fetch_add(1);
+        co_requests_.fetch_add((int64_t)batch.size());
+        lk.lock();
+        for (auto* p : batch) {
+            if (p == &me) continue;
+            p->ok = ok; p->err = err; p->done = true;
+            p->cv.notify_one();
+        }
+        if (mine) {
+            if (!ok) SetLastError(err);
+            return ok;
+        }
+        // my own request is still queued (it did not fit): lead the next batch right away
+        waited = true;
+        lead = true;
+    }
+}
+
+void ModelImpl::RunCoalesced(Loaded& st, const std::vector<Pending*>& batch) {
+    const b200::Plan& P = *st.plan;
+    const int G = (int)st.replicas.size();
+    std::vector<b200::Replica::Segment> segs(batch.size());
+    for (size_t k = 0; k < batch.size(); ++k) {
+        Pending& p = *batch[k];
+        b200::Replica::Segment& s = segs[k];
+        s.n = p.n;
+        s.in = p.ptrs;
+        std::vector<OutDesc>& outs = *p.outs;
+        s.out.assign(outs.size(), nullptr);
+        s.cap.assign(outs.size(), 0);
+        for (size_t i = 0; i < outs.size() && i < P.outputs.size(); ++i) {
+            const auto& t = P.tensors[P.outputs[i]];
+            outs[i].name = P.output_names[i];
+            outs[i].dims = P.output_dims[i];
+            outs[i].dims[0] = p.n;
+            outs[i].produced = (size_t)p.n * t.C * t.H * t.W * 4;
+            s.out[i] = outs[i].data;
+            s.cap[i] = outs[i].data ? outs[i].capacity : 0;
+        }
+    }
+    const int r = (int)(round_robin_.fetch_add(1) % (unsigned)G);
+    st.replicas[r]->RunSegments(segs, batch.front()->u8_mask);
 }
 
 // Shard planner (pure function, unit-tested on CPU through B200PlanShards): contiguous split of `n` samples

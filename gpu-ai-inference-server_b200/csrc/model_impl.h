@@ -2,6 +2,7 @@
 // so that ModelInfer can hand caller buffers to the GPU without intermediate copies.
 #pragma once
 #include <atomic>
+#include <condition_variable>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -61,6 +62,7 @@ public:
     };
     std::shared_ptr<Loaded> Pin() const;
     int staged_batch = 0;
+    void CoalesceStats(int64_t* batches, int64_t* requests) const { *batches = co_batches_.load(); *requests = co_requests_.load(); }
 
 private:
     bool ValidateInputs(const std::vector<IoDesc>& ins) const;
@@ -80,6 +82,27 @@ private:
     mutable std::mutex state_mu_;
     std::shared_ptr<Loaded> state_;
     std::atomic<unsigned> round_robin_{0};
+
+    // ---- request coalescer: concurrent small requests that arrive within a short window are
+    // executed as ONE batch.  Off unless config.json says "dynamic_batching": true or B200_ENGINE_COALESCE_US > 0.
+    struct Pending {
+        int n = 0;
+        unsigned u8_mask = 0;
+        std::vector<const void*> ptrs;
+        std::vector<OutDesc>* outs = nullptr;
+        bool done = false, ok = false, promoted = false;
+        std::string err;
+        std::condition_variable cv;
+    };
+    bool Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::vector<const void*>& ptrs, std::vector<OutDesc>& outs, unsigned u8_mask);
+    void RunCoalesced(Loaded& st, const std::vector<Pending*>& batch);
+    int coalesce_us_ = 0;      // collection window
+    int coalesce_small_ = 8;   // only requests of at most this many samples are coalesced
+    std::mutex co_mu_;
+    std::condition_variable co_cv_;
+    std::vector<Pending*> co_queue_;
+    bool co_leader_ = false;
+    std::atomic<int64_t> co_batches_{0}, co_requests_{0};
 };
 
 }  // namespace inference

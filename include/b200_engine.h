@@ -42,6 +42,8 @@ uint64_t B200KernelLaunchCount(void);
  * replica's own stream, max over replicas) to ms_out[0..iters).  If l2_flush != 0 a buffer larger
  * than L2 is overwritten between iterations (outside the event pair). */
 bool B200ModelStageInput(ModelHandle handle, const TensorData* input, ErrorMessage* error);
+/* Request coalescer counters: batches executed and requests they carried (requests / batches = mean coalesced size). */
+bool B200ModelCoalesceStats(ModelHandle handle, int64_t* batches, int64_t* requests);
 bool B200ModelForwardDevice(ModelHandle handle, int batch, int iters, int l2_flush, float* ms_out,
                             ErrorMessage* error);
 /* Copies the logits of the last B200ModelForwardDevice from replica 0 into `out` (fp32). */

@@ -337,6 +337,50 @@ def test_concurrent_callers_on_one_handle(pkg, repo_dir, monkeypatch):
         mgr.shutdown()
 
 
+def test_request_coalescer_batches_concurrent_callers(pkg, repo_dir, monkeypatch):
+    """concurrent batch-1 callers (what gin + the reference's /infer handler produce) are executed as
+    a few batches, every caller still gets exactly its own result, mixed request sizes and both input kinds included."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "bf16")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "16")
+    monkeypatch.setenv("B200_ENGINE_COALESCE_US", "3000")
+    u8 = synth.synthetic_images_u8(24, start=7000)
+    x = synth.to_model_input(u8)
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        want = np.concatenate([m.infer([pkg.TensorData("data_0", x[i:i + 12])], [pkg.OutputConfig("fc6_1", [12, 1000])])[0].data
+                               for i in (0, 12)])      # 12 > COALESCE_MAX_REQUEST: executed directly
+        b0, r0 = m.coalesce_stats()
+        assert (b0, r0) == (0, 0)
+        errs = []
+
+        def worker(i):
+            try:
+                for rep in range(3):
+                    k = 1 + (i + rep) % 2                      # requests of 1 or 2 images
+                    lo = (i + 5 * rep) % (24 - k)
+                    if (i + rep) % 3 == 0:                     # every third request sends raw uint8 pixels
+                        t = pkg.TensorData("data_0", np.ascontiguousarray(u8[lo:lo + k]), pkg.DataType.UINT8)
+                    else:
+                        t = pkg.TensorData("data_0", x[lo:lo + k])
+                    y = m.infer([t], [pkg.OutputConfig("fc6_1", [k, 1000])])[0].data
+                    if np.abs(y - want[lo:lo + k]).max() / np.abs(want).max() > 1e-5:
+                        errs.append((i, rep, "mismatch"))
+            except Exception as e:  # noqa: BLE001
+                errs.append((i, repr(e)))
+
+        ts = [threading.Thread(target=worker, args=(i,)) for i in range(24)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs[:3]
+        batches, requests = m.coalesce_stats()
+        assert requests == 24 * 3 and batches < requests / 2, (batches, requests)
+        assert m.get_stats().inference_count == 2 + 72
+    finally:
+        mgr.shutdown()
+
+
 def test_device_queries_and_vector_add(pkg):
     assert pkg.is_cuda_available() and pkg.get_device_count() >= 1
     info = pkg.get_device_info(0)
