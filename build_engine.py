@@ -45,7 +45,7 @@ def _compile(src: str, force: bool, hdr_t: float) -> str:
     sp = os.path.join(CSRC, src)
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), hdr_t):
         return obj
-    cmd = [NVCC, *COMMON, "-x", "cu", "-c", sp, "-o", obj]
+    cmd = [NVCC, *COMMON, *os.environ.get("B200_EXTRA_NVCC", "").split(), "-x", "cu", "-c", sp, "-o", obj]
     if src.endswith(".cu") and os.environ.get("B200_PTXAS_V"):
         cmd[1:1] = ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -505,6 +505,132 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) conv_simt_f32_kernel(Co
     }
 }
 
+// ------------------------------------------------------------------ fp32 implicit GEMM, second generation
+// Same arithmetic as conv_simt_f32_kernel (exact fp32 FFMA, prologue on in-bounds taps only) for the vectorisable case
+// (Cin, pitches, offsets multiples of 4).  The per-row pixel decode is hoisted out of the K loop, the next K slab is
+// prefetched into registers while the current one is multiplied, and the M tile shrinks (128/64/32) until the grid fills
+// the SMs - the old kernel ran batch-1 layers on 25-50 CTAs (13.4 ms per image).
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(256) conv_simt_f32_v2_kernel(ConvP p) {
+    constexpr int BK = 16;
+    static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+    constexpr int kASlots = BM * 4 / 256 > 0 ? BM * 4 / 256 : 1;  // float4 slots of the A tile per thread
+    constexpr bool kAHalf = BM * 4 < 256;                          // BM = 32: only the first 128 threads load A
+    constexpr bool kBHalf = BN * 4 < 256;                          // BN = 32: only the first 128 threads load B
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // ---- loader state: fixed (row, k quad) per thread
+    const int a_kq = (tid & 3) * 4;
+    int a_row[kASlots], a_ih0[kASlots], a_iw0[kASlots];
+    size_t a_base[kASlots];
+    bool a_ok[kASlots];
+#pragma unroll
+    for (int i = 0; i < kASlots; ++i) {
+        a_row[i] = (tid >> 2) + 64 * i;
+        const int m = m0 + a_row[i];
+        a_ok[i] = m < p.M && (!kAHalf || tid < BM * 4);
+        const int mm = a_ok[i] ? m : 0;
+        const int ow = mm % p.Wo, oh = (mm / p.Wo) % p.Ho, img = mm / (p.Wo * p.Ho);
+        a_ih0[i] = oh * p.stride - p.pad;
+        a_iw0[i] = ow * p.stride - p.pad;
+        a_base[i] = (size_t)img * p.H * p.W;
+    }
+    const int b_kk = tid / (BN / 4), b_nq = (tid % (BN / 4)) * 4;
+    const bool b_thread = !kBHalf || tid < BK * (BN / 4);
+    float4 ra[kASlots], rb;
+    auto fetch = [&](int k0) {
+        const int k = k0 + a_kq;
+        const int c = k % p.Cin, rs = k / p.Cin;
+        const int s = rs % p.S, r = rs / p.S;
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.pre_scale && k < p.K) {
+            sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + c));
+            sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + c));
+        }
+#pragma unroll
+        for (int i = 0; i < kASlots; ++i) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int ih = a_ih0[i] + r, iw = a_iw0[i] + s;
+            if (a_ok[i] && k < p.K && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+                v = __ldg(reinterpret_cast<const float4*>(p.in + (a_base[i] + (size_t)ih * p.W + iw) * p.in_pitch + p.in_coff + c));
+                if (p.pre_scale) {
+                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                }
+                if (p.pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            }
+            ra[i] = v;
+        }
+        rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int kb = k0 + b_kk, nn = n0 + b_nq;
+        if (b_thread && kb < p.K && nn < p.Cout) rb = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)kb * p.Cout + nn));
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    fetch(0);
+    for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < kASlots; ++i) {
+            if (!kAHalf || tid < BM * 4) {
+                As[a_kq + 0][a_row[i]] = ra[i].x; As[a_kq + 1][a_row[i]] = ra[i].y;
+                As[a_kq + 2][a_row[i]] = ra[i].z; As[a_kq + 3][a_row[i]] = ra[i].w;
+            }
+        }
+        if (b_thread) *reinterpret_cast<float4*>(&Bs[b_kk][b_nq]) = rb;
+        __syncthreads();
+        if (k0 + BK < p.K) fetch(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; j += 4) {
+                float4 tt = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + j]);
+                b[j] = tt.x; b[j + 1] = tt.y; b[j + 2] = tt.z; b[j + 3] = tt.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= p.M) continue;
+        float* orow = p.out + (size_t)m * p.out_pitch + p.out_coff;
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+            const int nn = n0 + tx * TN + j;
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float tt = acc[i][j + q];
+                if (p.bias && nn + q < p.Cout) tt += p.bias[nn + q];
+                if (p.post_relu) tt = fmaxf(tt, 0.f);
+                v[q] = tt;
+            }
+            if (p.vecC && nn + 3 < p.Cout) {
+                *reinterpret_cast<float4*>(orow + nn) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (nn + q < p.Cout) orow[nn + q] = v[q];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ rank-2 GEMM (classifier, MatMul/Gemm graphs)
 // out[m][n] = relu?(bias[n] + sum_k A[m][k] * W[k][n]); A rows are in_pitch apart, W is [K][Cout] row-major.
 // 32 x 64 output tile per CTA (2 x 4 per thread), K in steps of 32 with register prefetch of the next tiles, so a
@@ -603,6 +729,27 @@ cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t strea
     if (a.R == 1 && a.S == 1 && a.in.H == 1 && a.in.W == 1 && p.Ho == 1 && p.Wo == 1 && !a.pre_scale) {
         dim3 grid((p.M + 31) / 32, (a.Cout + 63) / 64);
         fc_f32_kernel<<<grid, 256, 0, stream>>>(p);
+    } else if (p.vecA && p.vecB && p.K % 4 == 0) {
+        // second-generation kernel: shrink the M tile until the grid covers the SMs
+        int sms = 148;
+        {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            int nsm = 0;
+            if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && nsm > 0) sms = nsm;
+        }
+        const bool narrow = a.Cout <= 32;
+        const int bn = narrow ? 32 : 64;
+        const int ntile = (a.Cout + bn - 1) / bn;
+        auto ctas = [&](int bm) { return ((p.M + bm - 1) / bm) * ntile; };
+        if (narrow) {
+            if (ctas(128) >= 2 * sms) conv_simt_f32_v2_kernel<128, 32, 4, 4><<<dim3((p.M + 127) / 128, ntile), 256, 0, stream>>>(p);
+            else conv_simt_f32_v2_kernel<64, 32, 2, 4><<<dim3((p.M + 63) / 64, ntile), 256, 0, stream>>>(p);
+        } else {
+            if (ctas(128) >= 2 * sms) conv_simt_f32_v2_kernel<128, 64, 8, 4><<<dim3((p.M + 127) / 128, ntile), 256, 0, stream>>>(p);
+            else if (ctas(64) >= sms) conv_simt_f32_v2_kernel<64, 64, 4, 4><<<dim3((p.M + 63) / 64, ntile), 256, 0, stream>>>(p);
+            else conv_simt_f32_v2_kernel<32, 64, 2, 4><<<dim3((p.M + 31) / 32, ntile), 256, 0, stream>>>(p);
+        }
     } else if (a.Cout <= 32) {
         constexpr int BM = 128, BN = 32;
         dim3 grid((p.M + BM - 1) / BM, (a.Cout + BN - 1) / BN);

@@ -71,6 +71,9 @@ __device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
 #ifndef B200_POLL_SLEEP_NS
 #define B200_POLL_SLEEP_NS 0
 #endif
+#ifndef B200_POLL_BACKOFF_AFTER
+#define B200_POLL_BACKOFF_AFTER 0
+#endif
 // Warp-collective wait (every lane of a CONVERGED warp must call it): lane 0 polls, backing off with nanosleep, the
 // other 31 lanes park at the warp barrier.  Measured on B200: try_wait returns after only ~60-80 cycles when the
 // phase is still pending, so 18 warps x 32 lanes polling at full speed made 30-55 % of all executed instructions
@@ -80,7 +83,7 @@ __device__ __forceinline__ void MbarWaitWarp(uint64_t* bar, uint32_t parity) {
         uint32_t spins = 0;
         while (!MbarTryWait(bar, parity)) {
 #if B200_POLL_SLEEP_NS > 0
-            __nanosleep(B200_POLL_SLEEP_NS);
+            if (spins >= B200_POLL_BACKOFF_AFTER) __nanosleep(B200_POLL_SLEEP_NS);
 #endif
             if (++spins > (1u << 24)) MbarTimeout();
         }
