@@ -448,10 +448,7 @@ void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std:
     // Large batches are pipelined in sub-batches: the H2D copy of sub-batch k+1 (copy stream) overlaps the forward
     // of sub-batch k (compute stream).  The fp32 NCHW input is 602 KB per image, so at bs256 the PCIe transfer is
     // as long as the whole forward; without overlap the two add up.
-    // uint8 pixels are 4x smaller than the fp32 tensor: their H2D (0.75 ms per 256 images) is cheaper than the efficiency two
-    // half-size forwards lose, so they are not split (measured: 3.05 ms unsplit vs 3.64 ms in two pieces)
-    static const bool chunk_forced = getenv("B200_ENGINE_PIPELINE_CHUNK") != nullptr;
-    const int chunk = (u8_mask && !chunk_forced) ? n : (pipeline_chunk_ > 0 ? pipeline_chunk_ : n);
+    const int chunk = pipeline_chunk_ > 0 ? pipeline_chunk_ : n;
     const int pieces = std::min<int>((n + chunk - 1) / chunk, (int)copy_events_.size());
     if (pieces <= 1) {
         for (size_t i = 0; i < P.inputs.size(); ++i)
