@@ -45,6 +45,14 @@ def _peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def _ncu_family_traffic(precision: str, batch: int):
+    """DRAM bytes (read + write) the conv family moved in ONE step according to ncu (`dram__bytes_read.sum +
+    dram__bytes_write.sum` summed over the family's 42 launches of one bs256 e4m3 forward, profiles/r01j_traffic_fp8.csv:
+    3.26 GB read + 0.61 GB written).  It is BELOW the algorithmic bytes because blocks 3/4 stay L2-resident and the bottleneck
+    tensor never leaves the SM there.  Only captured for the headline configuration; None otherwise."""
+    return 3.87e9 if (precision == "fp8" and batch == 256) else None
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled from a
     thread every 10 ms (nvidia-smi -lms is too coarse for a 50-100 ms timed region); falls back to one
@@ -304,7 +312,7 @@ def main():
                     "kernel": ("tcgen05 conv family: stem_conv7x7 / conv1x1_tma (+transition pool mode) / conv3x3_tma / dense_block megakernel"
                                if conv and conv[0].get("umma") else "conv_simt_f32_kernel"),
                     "launches_per_step": sum(1 for p in conv if p["ms"] > 0), "conv_layers_per_step": len(conv), "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "frac": gbs / peaks["hbm_gbs"], "traffic": _ncu_family_traffic(args.precision, B), "peak_source": peaks["source"],
                     "share_of_step": conv_ms / all_ms if all_ms else None,
                     "tensor": {"achieved_tflops": tfl, "peak_tflops": tensor_peak, "frac": tfl / tensor_peak,
                                "peak_note": "sustained measured bf16 cuBLAS x2 for fp8 / x0.5 for tf32-class; no fp8 peak was measured"},
