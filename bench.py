@@ -361,6 +361,10 @@ def main():
     barrier()
     if line is not None:
         print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
     return 0
 
 
