@@ -504,6 +504,10 @@ bool ModelImpl::Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::ve
         co_leader_ = true;
         auto queued = [&] { int s = 0; for (auto* p : co_queue_) s += p->n; return s; };
         if (!waited) co_cv_.wait_for(lk, std::chrono::microseconds(coalesce_us_), [&] { return queued() >= cap; });
+        // batch while busy: as long as every replica is already executing a batch, keep collecting - under load the batch
+        // grows to whatever arrives during one forward, when idle a request only ever waits its window
+        const int G = (int)st->replicas.size();
+        while (co_inflight_ >= G && queued() < cap) co_cv_.wait_for(lk, std::chrono::microseconds(100));
         // close the batch: queue order, same input kind as the first request, total <= cap
         std::vector<Pending*> batch, rest;
         int total = 0;
@@ -519,6 +523,7 @@ bool ModelImpl::Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::ve
             Pending* next = mine ? co_queue_.front() : &me;
             if (next != &me) { co_leader_ = true; next->promoted = true; next->cv.notify_one(); }
         }
+        ++co_inflight_;
         lk.unlock();
         std::string err;
         bool ok = true;
@@ -531,6 +536,8 @@ bool ModelImpl::Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::ve
         co_batches_.fetch_add(1);
         co_requests_.fetch_add((int64_t)batch.size());
         lk.lock();
+        --co_inflight_;
+        co_cv_.notify_all();  // a leader that kept collecting because every replica was busy may go now
         for (auto* p : batch) {
             if (p == &me) continue;
             p->ok = ok; p->err = err; p->done = true;

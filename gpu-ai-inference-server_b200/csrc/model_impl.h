@@ -102,6 +102,7 @@ private:
     std::condition_variable co_cv_;
     std::vector<Pending*> co_queue_;
     bool co_leader_ = false;
+    int co_inflight_ = 0;      // coalesced batches currently executing (guarded by co_mu_)
     std::atomic<int64_t> co_batches_{0}, co_requests_{0};
 };
 
