@@ -268,32 +268,49 @@ def main():
     assert np.isfinite(logits).all()
 
     # ---------------- end-to-end leg (host buffers through ModelInfer) ----------------
-    for _ in range(2):
-        model.infer([inp], outc)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        out = model.infer([inp], outc)[0].data
-    e2e_s = reduce_max(time.perf_counter() - t0)
-    barrier()
-    e2e_value = B * e2e_steps * n_gpus / e2e_s if not in_process_multi else B * e2e_steps / e2e_s
-    e2e_rel = float(np.abs(out - logits).max() / np.abs(logits).max())
+    # Every step is one blocking ModelInfer call: H2D of that step's pinned input, forward, D2H of its logits.  The headline
+    # runs the K calls from `E2E_CLIENTS` client threads (a server has several requests in flight; the engine keeps
+    # `instance_count` = 2 execution instances per GPU so one call's PCIe transfer overlaps another's forward); the
+    # strictly serial figure (one call at a time) is reported next to it.
+    import threading
+    E2E_CLIENTS = 2
+    e2e_steps = max(4, min(args.steps, 20))
+
+    def e2e_leg(make_input, clients):
+        ins = [make_input() for _ in range(clients)]
+        outs = [None] * clients
+        todo = [e2e_steps // clients + (1 if c < e2e_steps % clients else 0) for c in range(clients)]
+
+        def client(c, calls):
+            for _ in range(calls):
+                outs[c] = model.infer([ins[c]], outc)[0].data
+
+        def run(calls):
+            ths = [threading.Thread(target=client, args=(c, calls[c])) for c in range(1, clients)]
+            t0 = time.perf_counter()
+            for t in ths:
+                t.start()
+            client(0, calls[0])
+            for t in ths:
+                t.join()
+            return time.perf_counter() - t0
+
+        run([4] * clients)  # untimed: every execution instance this pattern reaches has its graphs and staging buffers
+        barrier()
+        dt = reduce_max(run(todo))
+        barrier()
+        return (B * e2e_steps * n_gpus / dt if not in_process_multi else B * e2e_steps / dt), outs[0]
+
+    e2e_serial, out = e2e_leg(lambda: pkg.TensorData("data_0", torch.from_numpy(x).pin_memory().numpy()), 1)
+    e2e_value, out2 = e2e_leg(lambda: pkg.TensorData("data_0", torch.from_numpy(x).pin_memory().numpy()), E2E_CLIENTS)
+    e2e_rel = float(max(np.abs(out - logits).max(), np.abs(out2 - logits).max()) / np.abs(logits).max())
 
     # ---------------- same call with raw uint8 HWC pixels (the section-8f ingestion extension: 4x fewer PCIe bytes) ----------------
-    u8 = np.concatenate([synth.synthetic_images_u8(min(B, 32), start=rank * 32)] * ((B + 31) // 32))[:B]
-    u8_pinned_t = torch.from_numpy(np.ascontiguousarray(u8)).pin_memory()
-    inp_u8 = pkg.TensorData("data_0", u8_pinned_t.numpy(), pkg.DataType.UINT8)
-    for _ in range(2):
-        out_u8 = model.infer([inp_u8], outc)[0].data
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        out_u8 = model.infer([inp_u8], outc)[0].data
-    u8_s = reduce_max(time.perf_counter() - t0)
-    barrier()
-    u8_value = B * e2e_steps * n_gpus / u8_s if not in_process_multi else B * e2e_steps / u8_s
-    u8_equal = bool(np.array_equal(out_u8, out))
+    u8 = np.ascontiguousarray(np.concatenate([synth.synthetic_images_u8(min(B, 32), start=rank * 32)] * ((B + 31) // 32))[:B])
+    mk_u8 = lambda: pkg.TensorData("data_0", torch.from_numpy(u8).pin_memory().numpy(), pkg.DataType.UINT8)  # noqa: E731
+    u8_serial, out_u8 = e2e_leg(mk_u8, 1)
+    u8_value, out_u8b = e2e_leg(mk_u8, E2E_CLIENTS)
+    u8_equal = bool(np.array_equal(out_u8, out) and np.array_equal(out_u8b, out))
 
     line = None
     if rank == 0:
@@ -351,9 +368,11 @@ def main():
                            "l2": "L2 flushed (256 MiB write) before every timed step; activation arena > L2"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(B * 1000 * 4),
-                        "steps": e2e_steps, "api": "ModelInfer (C-ABI) with pinned host buffers", "max_rel_vs_device_leg": e2e_rel},
+                        "steps": e2e_steps, "api": "ModelInfer (C-ABI) with pinned host buffers", "requests_in_flight": E2E_CLIENTS,
+                        "serial_value": e2e_serial, "max_rel_vs_device_leg": e2e_rel},
                 "e2e_uint8": {"value": u8_value, "unit": UNIT, "h2d_bytes_per_step": int(u8.nbytes), "d2h_bytes_per_step": int(B * 1000 * 4),
-                              "steps": e2e_steps, "api": "ModelInfer with DATATYPE_UINT8 [N,H,W,3] pixels (extension; value/255 + layout on the GPU)",
+                              "steps": e2e_steps, "requests_in_flight": E2E_CLIENTS, "serial_value": u8_serial,
+                              "api": "ModelInfer with DATATYPE_UINT8 [N,H,W,3] pixels (extension; value/255 + layout on the GPU)",
                               "logits_identical_to_float_path": u8_equal},
                 "roofline": roofline, "cpu_baseline": cpu, "latency": lat,
                 "wall_clock_check_ms_per_step": 1e3 * t_wall / args.steps}

@@ -106,7 +106,7 @@ EXPORTED_SYMBOLS = [
 ]
 EXTENSION_SYMBOLS = [
     "B200EngineVersion", "B200PlanDescribe", "B200PlanShards", "B200KernelLaunchCount", "B200ModelStageInput", "B200ModelForwardDevice",
-    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats",
+    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats", "B200HostAlloc", "B200HostFree",
 ]
 
 
@@ -148,6 +148,7 @@ def load_library() -> C.CDLL:
         "B200ModelProfileSteps": (vp, [vp, i, i, err]),
         "B200ModelReadValue": (C.c_int64, [vp, cp, C.POINTER(C.c_float), sz, err]),
         "B200ModelCoalesceStats": (b, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+        "B200HostAlloc": (vp, [sz]), "B200HostFree": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == missing export

@@ -35,6 +35,18 @@ std::shared_ptr<inference::ModelImpl::Loaded> PinHandle(ModelHandle h, std::shar
 
 extern "C" {
 
+void* B200HostAlloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void B200HostFree(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 const char* B200EngineVersion(void) { return "b200-engine 0.1 sm_100a"; }
 
 char* B200PlanDescribe(const char* model_dir, const char* precision, int max_batch, ErrorMessage* error) {

@@ -65,8 +65,57 @@ uint16_t F32ToBf16(float f) {
 }  // namespace
 
 // --------------------------------------------------------------------------------------------
-Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
-    : device_(device), plan_(std::move(plan)), use_graphs_(use_graphs) {
+ComputeChain::ComputeChain(int dev) : device(dev) {
+    DeviceGuard g(device);
+    CudaCheck(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate(chain)");
+}
+ComputeChain::~ComputeChain() {
+    if (ev) { cudaSetDevice(device); cudaEventDestroy(ev); }
+}
+
+PinnedPool& PinnedPool::Get() {
+    static PinnedPool* pool = new PinnedPool();  // leaked on purpose: request threads may outlive static destruction
+    return *pool;
+}
+PinnedPool::~PinnedPool() {}
+bool PinnedPool::IsPageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+void* PinnedPool::Take(size_t bytes) {
+    size_t cap = 1u << 20;
+    while (cap < bytes) cap <<= 1;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!budget_) {
+            const char* e = getenv("B200_ENGINE_STAGING_MB");
+            budget_ = (size_t)std::max(1, e ? atoi(e) : 2048) << 20;
+        }
+        for (auto& b : bufs_)
+            if (!b.used && b.cap == cap) { b.used = true; return b.p; }
+        if (total_ + cap > budget_) return nullptr;
+        total_ += cap;
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(mu_);
+        total_ -= cap;
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(mu_);
+    bufs_.push_back({p, cap, true});
+    return p;
+}
+void PinnedPool::Give(void* p) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& b : bufs_)
+        if (b.p == p) { b.used = false; return; }
+}
+
+Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, std::shared_ptr<ComputeChain> chain)
+    : device_(device), plan_(std::move(plan)), use_graphs_(use_graphs), chain_(std::move(chain)) {
     DeviceGuard g(device_);
     cudaDeviceProp prop;
     CudaCheck(cudaGetDeviceProperties(&prop, device_), "cudaGetDeviceProperties");
@@ -79,6 +128,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs)
     copy_events_.resize(32);
     for (auto& e : copy_events_) CudaCheck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     if (const char* pc = getenv("B200_ENGINE_PIPELINE_CHUNK")) pipeline_chunk_ = atoi(pc);
+    if (const char* pc = getenv("B200_ENGINE_CHAIN_MIN_BATCH")) chain_min_batch_ = atoi(pc);
     CudaCheck(cudaEventCreate(&ev0_), "cudaEventCreate");
     CudaCheck(cudaEventCreate(&ev1_), "cudaEventCreate");
     CudaCheck(cudaMalloc((void**)&arena_, plan_->arena_bytes + 4096), "cudaMalloc(arena)");
@@ -424,7 +474,7 @@ void Replica::Enqueue(int n, int off, unsigned u8_mask) {
 }
 
 void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
-                  const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask) {
+                  const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask, bool alone) {
     std::lock_guard<std::mutex> lk(mu_);
     DeviceGuard g(device_);
     const Plan& P = *plan_;
@@ -448,12 +498,26 @@ void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std:
     // Large batches are pipelined in sub-batches: the H2D copy of sub-batch k+1 (copy stream) overlaps the forward
     // of sub-batch k (compute stream).  The fp32 NCHW input is 602 KB per image, so at bs256 the PCIe transfer is
     // as long as the whole forward; without overlap the two add up.
-    const int chunk = pipeline_chunk_ > 0 ? pipeline_chunk_ : n;
+    const int chunk = pipeline_chunk_ > 0 && alone ? pipeline_chunk_ : n;
     const int pieces = std::min<int>((n + chunk - 1) / chunk, (int)copy_events_.size());
+    std::unique_lock<std::mutex> chain_lk;
+    const bool chained = chain_ && n >= chain_min_batch_;
+    auto chain_begin = [&] {
+        if (!chained) return;
+        chain_lk = std::unique_lock<std::mutex>(chain_->mu);
+        CudaCheck(cudaStreamWaitEvent(stream_, chain_->ev, 0), "chain wait");
+    };
+    auto chain_end = [&] {
+        if (!chained) return;
+        CudaCheck(cudaEventRecord(chain_->ev, stream_), "chain record");
+        chain_lk.unlock();
+    };
     if (pieces <= 1) {
         for (size_t i = 0; i < P.inputs.size(); ++i)
             CudaCheck(cudaMemcpyAsync(in_dst(i), host_inputs[i], (size_t)n * in_stride(i), cudaMemcpyHostToDevice, stream_), "H2D input");
+        chain_begin();
         Enqueue(n, 0, u8_mask);
+        chain_end();
     } else {
         const int per = (n + pieces - 1) / pieces;
         for (int k = 0; k < pieces; ++k) {
@@ -466,12 +530,14 @@ void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std:
             }
             CudaCheck(cudaEventRecord(copy_events_[k], copy_stream_), "event record");
         }
+        chain_begin();
         for (int k = 0; k < pieces; ++k) {
             const int off = k * per, cnt = std::min(per, n - off);
             if (cnt <= 0) break;
             CudaCheck(cudaStreamWaitEvent(stream_, copy_events_[k], 0), "stream wait event");
             Enqueue(cnt, off, u8_mask);
         }
+        chain_end();
     }
     for (size_t i = 0; i < P.outputs.size() && i < host_outputs.size(); ++i) {
         const TensorDesc& t = P.tensors[P.outputs[i]];
@@ -513,7 +579,16 @@ void Replica::RunSegments(const std::vector<Segment>& segs, unsigned u8_mask) {
         }
         off += s.n;
     }
-    Enqueue(total, 0, u8_mask);
+    {
+        std::unique_lock<std::mutex> chain_lk;
+        const bool chained = chain_ && total >= chain_min_batch_;
+        if (chained) {
+            chain_lk = std::unique_lock<std::mutex>(chain_->mu);
+            CudaCheck(cudaStreamWaitEvent(stream_, chain_->ev, 0), "chain wait");
+        }
+        Enqueue(total, 0, u8_mask);
+        if (chained) CudaCheck(cudaEventRecord(chain_->ev, stream_), "chain record");
+    }
     off = 0;
     for (const auto& s : segs) {
         for (size_t i = 0; i < P.outputs.size() && i < s.out.size(); ++i) {

@@ -21,9 +21,38 @@ struct CudaError : public std::runtime_error {
 };
 void CudaCheck(cudaError_t e, const char* what);
 
+// Execution instances of one GPU run their FORWARDS one after the other (their host<->device copies overlap freely): the
+// tcgen05 kernels are persistent one-CTA-per-SM kernels chained with programmatic dependent launch, and two such chains
+// interleaved on the same SMs park each other's pre-launched CTAs (measured: two concurrent forwards took 1.6x as long each).
+// The chain is a device-side event hand-over between the instances' streams; the host never blocks on it.
+struct ComputeChain {
+    explicit ComputeChain(int device);
+    ~ComputeChain();
+    std::mutex mu;
+    cudaEvent_t ev = nullptr;
+    int device;
+};
+
+// Process-wide pool of page-locked staging buffers: a request whose input lies in pageable memory (cgo's C.malloc) is
+// copied into one by the CALLER's thread before it queues for a GPU, so the slow pageable leg runs in parallel across request
+// threads instead of inside the driver's serial staging path while an execution instance is held.
+class PinnedPool {
+public:
+    static PinnedPool& Get();
+    static bool IsPageable(const void* p);
+    void* Take(size_t bytes);  // nullptr when the budget (B200_ENGINE_STAGING_MB, default 2048) is exhausted
+    void Give(void* p);
+    ~PinnedPool();
+private:
+    struct Buf { void* p; size_t cap; bool used; };
+    std::mutex mu_;
+    std::vector<Buf> bufs_;
+    size_t total_ = 0, budget_ = 0;
+};
+
 class Replica {
 public:
-    Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs);
+    Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, std::shared_ptr<ComputeChain> chain = nullptr);
     ~Replica();
     Replica(const Replica&) = delete;
     Replica& operator=(const Replica&) = delete;
@@ -36,8 +65,10 @@ public:
     // D2H of every graph output (min(capacity, produced) bytes each).  Blocking.  Thread-safe (serialised).
     // `u8_mask` bit i: graph input i is raw uint8 [n][H][W][C] pixels (value / 255 is applied on the GPU) instead of the
     // graph's fp32 NCHW tensor - the uint8-ingestion extension of SURVEY.md section 8f.
+    // `alone` = no other execution instance of this GPU is busy: only then is the batch cut into H2D/forward sub-batches
+    // (with other requests in flight their forwards already hide this one's copy, and whole batches run more efficiently).
     void Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
-             const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask = 0);
+             const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask = 0, bool alone = true);
 
     // Several callers' requests as ONE batch (request coalescing): every segment's inputs are
     // copied from its own host buffers to consecutive sample offsets, one forward of the total runs, and every segment's
@@ -92,9 +123,11 @@ private:
     int device_;
     std::shared_ptr<const Plan> plan_;
     bool use_graphs_;
+    std::shared_ptr<ComputeChain> chain_;
     cudaStream_t stream_ = nullptr;
     cudaStream_t copy_stream_ = nullptr;  // H2D of later sub-batches overlaps the forward of earlier ones
     std::vector<cudaEvent_t> copy_events_;
+    int chain_min_batch_ = 64;  // forwards of fewer samples leave SMs free and may overlap other instances' (B200_ENGINE_CHAIN_MIN_BATCH)
     int pipeline_chunk_ = 128;  // sub-batch size of the H2D/compute pipeline (B200_ENGINE_PIPELINE_CHUNK, 0 = off)
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     char* arena_ = nullptr;

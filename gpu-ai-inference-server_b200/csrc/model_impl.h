@@ -57,8 +57,19 @@ public:
     // extension API (b200_engine.h)
     struct Loaded {
         std::shared_ptr<const b200::Plan> plan;
-        std::vector<std::unique_ptr<b200::Replica>> replicas;
+        std::vector<std::unique_ptr<b200::Replica>> replicas;  // one per GPU (instance 0)
         std::vector<float> last_ms;
+        // Further execution instances per GPU (the reference's dead `instance_count` field, model.h:70): each has its own
+        // stream, arena and graph cache, so the H2D copy of one caller's batch overlaps the forward of another's.
+        int instances = 1;
+        std::vector<std::unique_ptr<b200::Replica>> extra;  // [g * (instances - 1) + j]
+        std::mutex pick_mu;
+        std::condition_variable pick_cv;
+        std::vector<int> busy;                               // [g * instances + j]: 1 while a Run call owns the instance
+        std::vector<uint64_t> next_ticket, serving;          // per GPU: callers are served strictly first come, first served
+        int Slots() const { return (int)replicas.size() * instances; }
+        b200::Replica* Acquire(int g, int* slot, bool* alone = nullptr);  // blocks until an instance of GPU g is free (FIFO)
+        void Release(int slot);
     };
     std::shared_ptr<Loaded> Pin() const;
     int staged_batch = 0;
@@ -96,6 +107,7 @@ private:
     };
     bool Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::vector<const void*>& ptrs, std::vector<OutDesc>& outs, unsigned u8_mask);
     void RunCoalesced(Loaded& st, const std::vector<Pending*>& batch);
+    bool stage_pageable_ = true;  // copy pageable request buffers into pinned staging on the caller's thread
     int coalesce_us_ = 0;      // collection window
     int coalesce_small_ = 8;   // only requests of at most this many samples are coalesced
     std::mutex co_mu_;

@@ -59,6 +59,13 @@ char* B200ModelProfileSteps(ModelHandle handle, int batch, int repeats, ErrorMes
 int64_t B200ModelReadValue(ModelHandle handle, const char* value_name, float* out, size_t out_elems,
                            ErrorMessage* error);
 
+/* Page-locked host memory for request buffers (copy elimination at the boundary): a caller
+ * that fills buffers from B200HostAlloc (cgo: C.B200HostAlloc instead of C.malloc, inference_binding.go:670-700) lets
+ * ModelInfer DMA straight from / into them; pageable buffers work too but go through the driver's staging copy.
+ * NULL on failure.  B200HostFree(NULL) is a no-op. */
+void* B200HostAlloc(size_t bytes);
+void B200HostFree(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

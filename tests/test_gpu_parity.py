@@ -337,6 +337,53 @@ def test_concurrent_callers_on_one_handle(pkg, repo_dir, monkeypatch):
         mgr.shutdown()
 
 
+def test_execution_instances_mixed_sizes_pinned_and_pageable(pkg, repo_dir, monkeypatch):
+    """BASELINE.json configs[4]: mixed batch sizes arriving concurrently.  Four execution instances on one GPU (the reference's
+    dead `instance_count`), FIFO hand-out, forwards of big batches chained, pageable request buffers staged through the
+    pinned pool and pinned ones (B200HostAlloc) read in place - every caller gets exactly the logits a lone call gets."""
+    import ctypes
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "fp8")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "128")
+    monkeypatch.setenv("B200_ENGINE_DEVICES", "0")
+    monkeypatch.setenv("B200_ENGINE_INSTANCES", "4")
+    monkeypatch.setenv("B200_ENGINE_CHAIN_MIN_BATCH", "16")
+    sizes = [1, 3, 16, 40, 96, 128]
+    x = synth.to_model_input(synth.synthetic_images_u8(128, start=4100))
+    lib = pkg.load_library()
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        want = {s: m.infer([pkg.TensorData("data_0", x[:s])], [pkg.OutputConfig("fc6_1", [s, 1000])])[0].data.copy() for s in sizes}
+        # a pinned copy of the images from the engine's allocator
+        ptr = lib.B200HostAlloc(x.nbytes)
+        assert ptr
+        pinned = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=x.shape)
+        pinned[...] = x
+        errs = []
+
+        def worker(i):
+            try:
+                rng = np.random.default_rng(i)
+                for k in range(6):
+                    s = int(rng.choice(sizes))
+                    src = pinned if (i + k) % 2 else x
+                    y = m.infer([pkg.TensorData("data_0", src[:s])], [pkg.OutputConfig("fc6_1", [s, 1000])])[0].data
+                    if not np.array_equal(y, want[s]):
+                        errs.append((i, s, float(np.abs(y - want[s]).max())))
+            except Exception as e:  # noqa: BLE001
+                errs.append((i, repr(e)))
+
+        ts = [threading.Thread(target=worker, args=(i,)) for i in range(12)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs[:5]
+        lib.B200HostFree(ptr)
+        lib.B200HostFree(None)
+    finally:
+        mgr.shutdown()
+
+
 def test_request_coalescer_batches_concurrent_callers(pkg, repo_dir, monkeypatch):
     """concurrent batch-1 callers (what gin + the reference's /infer handler produce) are executed as
     a few batches, every caller still gets exactly its own result, mixed request sizes and both input kinds included."""
