@@ -460,6 +460,10 @@ bool DenseBlockGeometry(int H, int W, int* ipc, int* mt1) {
     int best = 0;
     for (int i = 1; i <= 8; ++i)
         if (i * HW <= 256 && i * SL <= 256) best = i;
+    if (const char* e = getenv("B200_DENSE_IPC")) {  // experiment: fewer images per CTA pass = more CTAs at work
+        const int v = atoi(e);
+        if (v >= 1 && v <= best) best = v;
+    }
     if (!best) return false;
     *ipc = best;
     *mt1 = (best * HW + 127) / 128;
@@ -470,6 +474,23 @@ cudaError_t DenseBlockFp8(const DenseBlockArgs& a, cudaStream_t stream) {
     int ipc = 0, mt1 = 0;
     if (!DenseBlockGeometry(a.H, a.W, &ipc, &mt1) || a.num_layers <= 0 || !a.layers_dev) return cudaErrorInvalidValue;
     if (a.n <= 0) return cudaSuccess;
+    // Images per CTA pass: the kernel is a per-unit latency chain, so what counts is the number of passes a CTA makes
+    // (waves) times the length of the chain, which grows with the conv1 M tiles.  Measured at bs256, 7x7: 3 images per pass
+    // (86 CTAs, 2 M tiles) 195 us, 2 per pass (128 CTAs, 1 M tile) 144 us, 1 per pass (2 waves) 276 us.
+    if (!getenv("B200_DENSE_IPC")) {
+        int sms = 148;
+        { int dev = 0, v = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v; }
+        const int HW = a.H * a.W;
+        double best_cost = 1e30;
+        int best_ipc = ipc;
+        for (int i = 1; i <= ipc; ++i) {
+            const int groups = (a.n + i - 1) / i, waves = (groups + sms - 1) / sms, tiles = (i * HW + 127) / 128;
+            const double cost = waves * (6.0 + 1.8 * tiles);
+            if (cost < best_cost - 1e-9) { best_cost = cost; best_ipc = i; }
+        }
+        ipc = best_ipc;
+        mt1 = (ipc * HW + 127) / 128;
+    }
     DbParams p;
     p.layers = a.layers_dev; p.num_layers = a.num_layers;
     p.buf = a.buf; p.pitch = a.pitch; p.n = a.n; p.H = a.H; p.W = a.W;

@@ -1,0 +1,16 @@
+for D in 0 1 2 3 4 8 12 15; do
+B200_DENSE_DBG=$D timeout 300 python - <<'P'
+import os, json, numpy as np
+os.environ["B200_ENGINE_PRECISION"]="fp8"; os.environ["B200_ENGINE_DEVICES"]="0"; os.environ["B200_ENGINE_INSTANCES"]="1"
+import __graft_entry__ as ge
+pkg=ge.load_package(); ge.ensure_fixtures()
+from tools import synth
+mgr=pkg.InferenceManager("models"); mgr.load_model("densenet_onnx"); m=mgr.get_model("densenet_onnx")
+x=synth.to_model_input(synth.synthetic_images_u8(32,start=0)); x=np.concatenate([x]*8)
+m.stage_input(pkg.TensorData("data_0",x))
+m.forward_device(256,3,True)
+prof=m.profile_steps(256,3)
+print("DBG",os.environ["B200_DENSE_DBG"], [round(p["ms"]*1e3,1) for p in prof if p["step"] in (2,15)])
+mgr.shutdown()
+P
+done
