@@ -264,6 +264,9 @@ bool ModelImpl::Load() {
         coalesce_us_ = atoi(EnvOr("B200_ENGINE_COALESCE_US", config_.dynamic_batching ? "200" : "0").c_str());
         coalesce_small_ = std::max(1, atoi(EnvOr("B200_ENGINE_COALESCE_MAX_REQUEST", "8").c_str()));
         stage_pageable_ = EnvOr("B200_ENGINE_STAGE_PAGEABLE", "1") != "0";
+        // a request is split over GPUs only in shards of at least this many samples (bs256 on 8 GPUs -> 32 each);
+        // smaller requests go whole to one GPU, round-robin, which is what keeps mixed concurrent traffic efficient
+        min_shard_ = std::max(1, atoi(EnvOr("B200_ENGINE_MIN_SHARD", "32").c_str()));
         precision_s = EnvOr("B200_ENGINE_PRECISION", precision_s);
         max_batch = atoi(EnvOr("B200_ENGINE_MAX_BATCH", std::to_string(max_batch)).c_str());
         if (max_batch < 1) max_batch = 1;
@@ -703,7 +706,7 @@ bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_pt
         outs[i].dims[0] = n;
         outs[i].produced = (size_t)n * out_stride[i];
     }
-    static const int kMinShard = std::max(1, atoi(EnvOr("B200_ENGINE_MIN_SHARD", "8").c_str()));
+    const int kMinShard = min_shard_;
     using Shard = ShardPlan;
     int rr = (int)(round_robin_.fetch_add(1) % (unsigned)G);
     std::vector<Shard> shards = PlanShards(n, G, max_b, kMinShard, rr);

@@ -107,6 +107,7 @@ private:
     };
     bool Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::vector<const void*>& ptrs, std::vector<OutDesc>& outs, unsigned u8_mask);
     void RunCoalesced(Loaded& st, const std::vector<Pending*>& batch);
+    int min_shard_ = 32;          // smallest per-GPU shard of a split request (B200_ENGINE_MIN_SHARD)
     bool stage_pageable_ = true;  // copy pageable request buffers into pinned staging on the caller's thread
     int coalesce_us_ = 0;      // collection window
     int coalesce_small_ = 8;   // only requests of at most this many samples are coalesced

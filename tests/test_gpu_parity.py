@@ -445,6 +445,7 @@ def test_multi_gpu_batch_sharding_matches_single_gpu(pkg, repo_dir, monkeypatch)
         pytest.skip("needs >= 2 GPUs")
     monkeypatch.setenv("B200_ENGINE_PRECISION", "bf16")
     monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "16")
+    monkeypatch.setenv("B200_ENGINE_MIN_SHARD", "8")
     n = 8 * g + 3
     x = synth.to_model_input(synth.synthetic_images_u8(n, start=5000))
     outs = {}
