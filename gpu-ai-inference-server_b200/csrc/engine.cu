@@ -295,6 +295,9 @@ void Replica::BuildDenseRuns() {
             const Step& b = P.steps[j + 1];
             const TensorDesc& ain = P.tensors[a.in];
             if (ain.buffer != first_in.buffer || ain.H != first_in.H || ain.W != first_in.W || ain.pitch != first_in.pitch) break;
+            // dense connectivity: every layer reads exactly its predecessor's inputs plus the 32 channels it appended (the
+            // dense-block kernel forwards those through shared memory)
+            if (!table.empty() && a.Cin != table.back().Cin + 32) break;
             kernels::DenseLayerDesc d;
             memset(&d, 0, sizeof(d));
             memcpy(&d.w1, prepared_[j].umma.tensor_map, sizeof(CUtensorMap));
