@@ -384,6 +384,40 @@ def test_execution_instances_mixed_sizes_pinned_and_pageable(pkg, repo_dir, monk
         mgr.shutdown()
 
 
+def test_fused_dense_layer_tile_kernel_is_bit_identical(pkg, repo_dir, monkeypatch):
+    """The opt-in fused dense-layer kernel (kernels_dense_tile.cu: conv1 A operand through tensor memory, bottleneck tensor in
+    shared memory, 14x14 tiles with halo recompute, zeroed out-of-image patch pixels) must reproduce the two-kernel path of the
+    56x56 and 28x28 blocks bit for bit - image borders, every tile position and the K tails (Cin 64..256) included."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "fp8")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "8")
+    monkeypatch.setenv("B200_ENGINE_DEVICES", "0")
+    monkeypatch.setenv("B200_ENGINE_INSTANCES", "1")
+    x = synth.to_model_input(synth.synthetic_images_u8(5, start=4300))
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("B200_ENGINE_TILEFUSE", flag)
+        mgr = pkg.InferenceManager(repo_dir)
+        try:
+            mgr.load_model("densenet_onnx")
+            m = mgr.get_model("densenet_onnx")
+            n0 = pkg.kernel_launch_count()
+            outs[flag] = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [5, 1000])])[0].data.copy()
+            launches = pkg.kernel_launch_count() - n0
+            # block 1 (6 layers) and the first 5 layers of block 2 (Cin <= 256): 22 launches become 11
+            outs["launches" + flag] = launches
+            # an intermediate tensor of block 1 too, not only the logits
+            try:
+                outs["feat" + flag] = m.read_value("/features/denseblock1/denselayer6/conv2/Conv_output_0", 5 * 32 * 56 * 56)
+            except pkg.EngineError:
+                outs["feat" + flag] = None
+        finally:
+            mgr.shutdown()
+    assert outs["launches1"] == outs["launches0"] - 11, (outs["launches0"], outs["launches1"])
+    assert np.array_equal(outs["0"], outs["1"])
+    if outs["feat0"] is not None and outs["feat1"] is not None:
+        assert outs["feat0"].size >= 32 * 56 * 56 and np.array_equal(outs["feat0"], outs["feat1"])
+
+
 def test_request_coalescer_batches_concurrent_callers(pkg, repo_dir, monkeypatch):
     """concurrent batch-1 callers (what gin + the reference's /infer handler produce) are executed as
     a few batches, every caller still gets exactly its own result, mixed request sizes and both input kinds included."""
