@@ -179,3 +179,14 @@ def test_planner_test_model_and_errors(pkg, repo_dir, tmp_path):
     onnx_lite.save(onnx_lite.Model(g), str(tmp_path / "m" / "model.onnx"))
     with pytest.raises(pkg.EngineError, match="unsupported operator 'Erf'"):
         pkg.plan_describe(str(tmp_path / "m"), "fp32", 1)
+
+
+def test_native_replay_tool_links_against_the_c_abi_only(tmp_path):
+    """tools/rest_replay.cpp is the stand-in for the Go REST handler (threads calling ModelInfer): it must compile against
+    include/ alone and link against nothing but libinference_engine.so; without a GPU it fails loudly at load, like the server."""
+    import subprocess
+    import build_engine
+    exe = build_engine.build_tools(quiet=True)
+    r = subprocess.run([exe, "--repo", str(tmp_path), "--requests", "1", "--threads", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "load failed" in r.stderr or "ModelInfer" in r.stderr or r.returncode == 1
