@@ -114,8 +114,10 @@ void PinnedPool::Give(void* p) {
         if (b.p == p) { b.used = false; return; }
 }
 
-Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, std::shared_ptr<ComputeChain> chain)
-    : device_(device), plan_(std::move(plan)), use_graphs_(use_graphs), chain_(std::move(chain)) {
+Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, std::shared_ptr<ComputeChain> chain, const Replica* weights_of)
+    : device_(device), plan_(std::move(plan)), use_graphs_(use_graphs), chain_(std::move(chain)), weights_of_(weights_of) {
+    if (weights_of_ && (weights_of_->device_ != device_ || weights_of_->plan_.get() != plan_.get()))
+        throw CudaError("a replica can only borrow the weights of a replica of the same plan on the same device");
     DeviceGuard g(device_);
     cudaDeviceProp prop;
     CudaCheck(cudaGetDeviceProperties(&prop, device_), "cudaGetDeviceProperties");
@@ -140,6 +142,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
     dconst_.assign(P.consts.size(), nullptr);
     auto vec = [&](int idx) -> const float* {
         if (idx < 0) return nullptr;
+        if (weights_of_) return weights_of_->dconst_[idx];
         if (!dconst_[idx]) dconst_[idx] = (const float*)Upload(P.consts[idx].data.data(), P.consts[idx].data.size() * 4);
         return dconst_[idx];
     };
@@ -174,6 +177,12 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         const std::vector<float>& w = P.consts[s.weight].data;  // [Cout][R][S][Cin]
         const int K = s.R * s.S * s.Cin;
         pr.use_umma = s.stem_nchw || pr.in.dtype != DType::F32;
+        if (weights_of_) {  // same plan, same device: the lender's packed weights, scales and tensor map serve this instance too
+            const Prepared& lp = weights_of_->prepared_[i];
+            pr.w_kn = lp.w_kn;
+            pr.umma = lp.umma;
+            continue;
+        }
         if (!pr.use_umma) {
             std::vector<float> kn((size_t)K * s.Cout);
             for (int o = 0; o < s.Cout; ++o)
@@ -242,9 +251,18 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         }
         pr.umma.tensor_map = tm;
     }
-    BuildDenseRuns();
+    if (weights_of_) BorrowDenseRuns(*weights_of_);
+    else BuildDenseRuns();
     flush_bytes_ = 256u << 20;
     CudaCheck(cudaStreamSynchronize(stream_), "replica init");
+}
+
+// The dense-layer tables hold only weights (tensor maps, packed BN constants, epilogue vectors): an execution instance that
+// borrows another's weight set reuses them and points the runs at its OWN arena.
+void Replica::BorrowDenseRuns(const Replica& lender) {
+    dense_runs_ = lender.dense_runs_;
+    for (size_t i = 0; i < prepared_.size(); ++i) prepared_[i].fused_run = lender.prepared_[i].fused_run;
+    for (DenseRun& run : dense_runs_) run.args.buf = BufferPtr(plan_->tensors[plan_->steps[run.first_step].in].buffer);
 }
 
 // Finds maximal runs of dense layers (conv1x1 -> 128 channels -> conv3x3 -> 32 channels appended to the buffer the 1x1
@@ -346,8 +364,9 @@ Replica::~Replica() {
     if (copy_stream_) { cudaStreamSynchronize(copy_stream_); cudaStreamDestroy(copy_stream_); }
     for (auto& e : copy_events_) if (e) cudaEventDestroy(e);
     for (auto& kv : graphs_) cudaGraphExecDestroy(kv.second);
-    for (auto& pr : prepared_)
-        if (pr.umma.tensor_map) delete (CUtensorMap*)pr.umma.tensor_map;
+    if (!weights_of_)
+        for (auto& pr : prepared_)
+            if (pr.umma.tensor_map) delete (CUtensorMap*)pr.umma.tensor_map;
     for (void* p : allocations_) cudaFree(p);
     if (flush_buf_) cudaFree(flush_buf_);
     if (arena_) cudaFree(arena_);

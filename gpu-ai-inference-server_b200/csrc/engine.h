@@ -52,7 +52,11 @@ private:
 
 class Replica {
 public:
-    Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, std::shared_ptr<ComputeChain> chain = nullptr);
+    // `weights_of`: another Replica of the SAME plan on the SAME device whose device-resident weights, constants, tensor maps and
+    // dense-layer tables this one borrows (execution instances of one GPU share one read-only weight copy: one upload, one
+    // quantisation pass, one L2 footprint).  The lender must outlive the borrower.
+    Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, std::shared_ptr<ComputeChain> chain = nullptr,
+            const Replica* weights_of = nullptr);
     ~Replica();
     Replica(const Replica&) = delete;
     Replica& operator=(const Replica&) = delete;
@@ -117,6 +121,7 @@ private:
     size_t EnqueueAt(size_t i, int n, int off, unsigned u8_mask = 0);
     const uint8_t* U8Source(int tensor, int off, unsigned u8_mask);  // device uint8 staging of a graph input, or null  // runs step i (or the fused run starting there); returns steps consumed
     void BuildDenseRuns();
+    void BorrowDenseRuns(const Replica& lender);
     kernels::View MakeView(int tensor) const;
     void* BufferPtr(int buffer) const;
     void* Upload(const void* host, size_t bytes);
@@ -125,6 +130,7 @@ private:
     std::shared_ptr<const Plan> plan_;
     bool use_graphs_;
     std::shared_ptr<ComputeChain> chain_;
+    const Replica* weights_of_ = nullptr;  // lender of the weight set, or null when this replica owns its own
     cudaStream_t stream_ = nullptr;
     cudaStream_t copy_stream_ = nullptr;  // H2D of later sub-batches overlaps the forward of earlier ones
     std::vector<cudaEvent_t> copy_events_;

@@ -293,7 +293,7 @@ bool ModelImpl::Load() {
         for (size_t di = 0; di < devices.size(); ++di)
             for (int j = 1; j < st->instances; ++j) {
                 const int d = devices[di];
-                st->extra.emplace_back(new b200::Replica(d, plan, graphs, chains[di]));
+                st->extra.emplace_back(new b200::Replica(d, plan, graphs, chains[di], st->replicas[di].get()));
                 mem += st->extra.back()->DeviceBytes();
             }
         st->busy.assign(st->replicas.size() * st->instances, 0);
