@@ -253,6 +253,35 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
     }
     if (weights_of_) BorrowDenseRuns(*weights_of_);
     else BuildDenseRuns();
+    // Wide transition layers (Cout > 128): conv1x1_tma redoes the pooled transform of the A tile for every 128-column N tile;
+    // materialising sum_2x2 relu(bn(x)) once and running a plain 1x1 conv over it is cheaper (kernels_poolbn.cu).
+    {
+        const char* e = getenv("B200_ENGINE_SPLIT_TRANSITION");
+        const bool enabled = !(e && e[0] == '0');
+        size_t need = 0;
+        for (size_t i = 0; enabled && i < P.steps.size(); ++i) {
+            const Step& s = P.steps[i];
+            Prepared& pr = prepared_[i];
+            if (s.kind != StepKind::Conv || !s.pool2_fused || !pr.use_umma || s.Cout <= 128 || pr.fused_run >= 0) continue;
+            kernels::View vin = pr.in;
+            vin.C = s.Cin;
+            kernels::View pooled = vin;
+            pooled.base = arena_;  // any 16-byte aligned address: only the geometry is checked here
+            pooled.H = pr.out.H; pooled.W = pr.out.W; pooled.pitch = s.Cin; pooled.c_off = 0;
+            kernels::ConvArgs a2 = pr.conv;
+            a2.in = pooled;
+            a2.pre_scale = a2.pre_shift = nullptr;
+            a2.pre_relu = false; a2.pool2 = false; a2.out_mul = 0.25f;
+            if (!pr.conv.pre_scale || !kernels::PoolBnRelu2x2Supported(vin, pooled) || !kernels::Conv1x1TmaSupported(a2)) continue;
+            pr.split_pool = true;
+            need = std::max(need, (size_t)P.max_batch * pooled.H * pooled.W * s.Cin * DTypeSize(vin.dtype) + 256);
+        }
+        if (need) {
+            CudaCheck(cudaMalloc(&pool_scratch_, need), "cudaMalloc(pooled transition operand)");
+            allocations_.push_back(pool_scratch_);
+            device_bytes_ += need;
+        }
+    }
     flush_bytes_ = 256u << 20;
     CudaCheck(cudaStreamSynchronize(stream_), "replica init");
 }
@@ -433,6 +462,20 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
             a.out = vout;
             a.n = n;
             a.in_u8_hwc = u8;
+            if (pr0.split_pool) {
+                kernels::View src = vin;
+                src.C = s.Cin;
+                kernels::View pooled = src;
+                pooled.base = pool_scratch_;
+                pooled.H = vout.H; pooled.W = vout.W; pooled.pitch = s.Cin; pooled.c_off = 0;
+                e = kernels::PoolBnRelu2x2(src, pooled, n, a.pre_scale, a.pre_shift, a.pre_relu, stream_);
+                if (e != cudaSuccess) break;
+                a.in = pooled;
+                a.pre_scale = a.pre_shift = nullptr;
+                a.pre_relu = false; a.pool2 = false; a.out_mul = 0.25f;
+                e = kernels::Conv1x1Tma(a, pr0.umma, stream_);
+                break;
+            }
             e = pr0.use_umma ? kernels::ConvUmma(a, pr0.umma, stream_) : kernels::ConvSimtF32(a, pr0.w_kn, stream_);
             break;
         }

@@ -105,6 +105,7 @@ private:
         const float* shift = nullptr;
         size_t in_io_stride = 0, in2_io_stride = 0, out_io_stride = 0;  // bytes per sample when the view is graph I/O
         int fused_run = -1;  // index into dense_runs_ when this step starts a run executed by the dense-block kernel
+        bool split_pool = false;  // wide transition: pooled BN+ReLU A operand materialised once, then a plain 1x1 conv
     };
     // Consecutive (1x1 conv, 3x3 conv) step pairs of one dense block executed by ONE persistent kernel.
     struct DenseRun {
@@ -139,6 +140,7 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     char* arena_ = nullptr;
     void* flush_buf_ = nullptr;
+    void* pool_scratch_ = nullptr;  // [max_batch][Ho][Wo][Cin] of the widest split transition
     size_t flush_bytes_ = 0;
     std::vector<void*> allocations_;
     std::vector<const float*> dconst_;  // fp32 device copy of every Plan::consts entry that is used as a vector

@@ -34,6 +34,7 @@ struct ConvArgs {
     const float* bias = nullptr;  // [Cout]
     bool post_relu = false;
     bool pool2 = false;  // A rows are 2x2 averages of (prologue-transformed) input pixels
+    float out_mul = 1.f; // extra factor on the per-channel output scale (0.25 when the caller pooled the A operand itself)
     bool stem_nchw = false;  // `in` is the caller's fp32 NCHW image batch (7x7/s2/p3 stem, see kernels_stem.cu)
     const uint8_t* in_u8_hwc = nullptr;  // stem_nchw only: read raw uint8 [n][H][W][C] pixels instead (value / 255)
 };
@@ -73,6 +74,11 @@ cudaError_t Conv3x3Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
 // 1x1/s1 conv with TMA loads/stores and an in-place BN+ReLU transform of the landed A tile (kernels_conv1x1.cu)
 bool Conv1x1TmaSupported(const ConvArgs& a);
 cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
+
+// Wide transition layers: sum over 2x2 of relu(bn(x)) written once as the MMA element type (kernels_poolbn.cu); the conv that
+// follows runs without prologue and with ConvArgs::out_mul = 0.25.  Bit-identical to the pooled transform of Conv1x1Tma.
+bool PoolBnRelu2x2Supported(View in, View out);
+cudaError_t PoolBnRelu2x2(View in, View out, int n, const float* scale, const float* shift, bool relu, cudaStream_t stream);
 
 // ---- a whole dense block in one persistent kernel (kernels_dense.cu; e4m3, whole images per CTA) ----
 struct DenseLayerDesc {          // one BN-ReLU-Conv1x1(->128)-BN-ReLU-Conv3x3(->32) layer; lives in device memory

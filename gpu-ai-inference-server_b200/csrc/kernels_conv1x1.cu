@@ -450,7 +450,7 @@ cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
     const int bn = a.Cout <= 64 ? 64 : 128;
     p.num_n_tiles = a.Cout / bn;
     p.num_chunks = (a.Cin + ch - 1) / ch;
-    p.tile_rows = kTileM; p.pool_k = 0; p.out_scale_mul = 1.f;
+    p.tile_rows = kTileM; p.pool_k = 0; p.out_scale_mul = a.out_mul;
     p.num_m_tiles = (p.M + kTileM - 1) / kTileM;
     TensorMap tin, tout;
     if (a.pool2) {

@@ -418,6 +418,31 @@ def test_fused_dense_layer_tile_kernel_is_bit_identical(pkg, repo_dir, monkeypat
         assert outs["feat0"].size >= 32 * 56 * 56 and np.array_equal(outs["feat0"], outs["feat1"])
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp8"])
+def test_split_wide_transitions_are_bit_identical(pkg, repo_dir, monkeypatch, precision):
+    """Transitions 2 and 3 (Cout 256 / 512) run as pooled-BN-ReLU pass + plain 1x1 conv (kernels_poolbn.cu) instead of redoing the
+    pooled transform per N tile inside conv1x1_tma<POOL>: same packed arithmetic, same summation order, same logits."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", precision)
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "8")
+    monkeypatch.setenv("B200_ENGINE_DEVICES", "0")
+    monkeypatch.setenv("B200_ENGINE_INSTANCES", "1")
+    x = synth.to_model_input(synth.synthetic_images_u8(6, start=4400))
+    outs, launches = {}, {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("B200_ENGINE_SPLIT_TRANSITION", flag)
+        mgr = pkg.InferenceManager(repo_dir)
+        try:
+            mgr.load_model("densenet_onnx")
+            m = mgr.get_model("densenet_onnx")
+            n0 = pkg.kernel_launch_count()
+            outs[flag] = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [6, 1000])])[0].data.copy()
+            launches[flag] = pkg.kernel_launch_count() - n0
+        finally:
+            mgr.shutdown()
+    assert launches["1"] == launches["0"] + 2, launches   # two transitions gained a kernel each
+    assert np.array_equal(outs["0"], outs["1"])
+
+
 def test_request_coalescer_batches_concurrent_callers(pkg, repo_dir, monkeypatch):
     """concurrent batch-1 callers (what gin + the reference's /infer handler produce) are executed as
     a few batches, every caller still gets exactly its own result, mixed request sizes and both input kinds included."""
