@@ -709,6 +709,70 @@ __global__ void __launch_bounds__(256) fc_f32_kernel(ConvP p) {
     }
 }
 
+// Same product with a three-deep cp.async pipeline (the register-prefetch kernel above keeps ONE 32-step K slab in flight and is
+// bound by global-load latency: 41 us for batch 256 x 1000 classes x K 1024).  Every output is still accumulated by one thread
+// with k ascending, so the result is bit-identical.  Needs 16-byte aligned rows (vecA, vecB) and K % 32 == 0.
+__device__ __forceinline__ void FcCpAsync16(float* smem_dst, const float* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__global__ void __launch_bounds__(256) fc_f32_pipelined_kernel(ConvP p) {
+    constexpr int BM = 32, BN = 64, BK = 32, ST = 3;
+    __shared__ __align__(16) float As[ST][BM][BK + 4];
+    __shared__ __align__(16) float Bs[ST][BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int a_row = tid >> 3, a_k = (tid & 7) * 4;   // A: 32 rows x 8 quads
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;    // B: two (k row, n quad) pieces per thread
+    const int nk = p.K / BK;
+    auto issue = [&](int it) {
+        if (it < nk) {
+            const int k0 = it * BK, st = it % ST;
+            const int m = m0 + a_row;
+            const bool ok = m < p.M;
+            FcCpAsync16(&As[st][a_row][a_k], ok ? p.in + (size_t)m * p.in_pitch + p.in_coff + k0 + a_k : p.in, ok);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = k0 + b_k + 16 * h;
+                const bool okb = n0 + b_n + 3 < p.Cout;
+                FcCpAsync16(&Bs[st][b_k + 16 * h][b_n], okb ? p.w + (size_t)k * p.Cout + n0 + b_n : p.w, okb);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float acc[2][4] = {};
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) issue(s);
+    for (int it = 0; it < nk; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(ST - 2) : "memory");
+        __syncthreads();               // slab `it` has landed for every thread; slab it-1's buffer is free again
+        issue(it + ST - 1);
+        const int st = it % ST;
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float a0 = As[st][ty * 2][kk], a1 = As[st][ty * 2 + 1][kk];
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[st][kk][tx * 4]);
+            acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+            acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+            acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+            acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int m = m0 + ty * 2 + i;
+        if (m >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= p.Cout) continue;
+            float v = acc[i][j] + (p.bias ? p.bias[n] : 0.f);
+            if (p.post_relu) v = fmaxf(v, 0.f);
+            p.out[(size_t)m * p.out_pitch + p.out_coff + n] = v;
+        }
+    }
+}
+
 }  // namespace
 
 // ====================================================================== launchers
@@ -728,7 +792,8 @@ cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t strea
     if (p.M <= 0) return cudaSuccess;
     if (a.R == 1 && a.S == 1 && a.in.H == 1 && a.in.W == 1 && p.Ho == 1 && p.Wo == 1 && !a.pre_scale) {
         dim3 grid((p.M + 31) / 32, (a.Cout + 63) / 64);
-        fc_f32_kernel<<<grid, 256, 0, stream>>>(p);
+        if (p.vecA && p.vecB && p.K % 32 == 0 && p.K >= 128) fc_f32_pipelined_kernel<<<grid, 256, 0, stream>>>(p);
+        else fc_f32_kernel<<<grid, 256, 0, stream>>>(p);
     } else if (p.vecA && p.vecB && p.K % 4 == 0) {
         // second-generation kernel: shrink the M tile until the grid covers the SMs
         int sms = 148;
