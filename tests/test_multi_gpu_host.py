@@ -52,12 +52,24 @@ print("RANK_OK", rank, flush=True)
 '''
 
 
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:  # a fixed port collided with a run moments earlier (TIME_WAIT)
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def _torchrun(args, env_extra=None, timeout=300):
     env = dict(os.environ)
     env.update(env_extra or {})
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", *args]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    r = None
+    for _ in range(2):  # one retry: the rendezvous port can still be taken between the probe and the launch
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", str(_free_port()), *args]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        if r.returncode == 0:
+            break
+    return r
 
 
 def test_bench_dist_helpers_with_gloo_world_size_2(tmp_path):
