@@ -9,6 +9,15 @@
  *   env B200_ENGINE_MAX_BATCH = per-GPU arena batch     (default 256).
  *   `config.json` next to model.onnx may carry "precision" / "max_batch_size" with the same
  *   meaning (environment wins).
+ * Serving knobs (all read at Model::Load):
+ *   env B200_ENGINE_INSTANCES       = execution instances per GPU, 1..8 (default 4; `instance_count` of ModelConfig/config.json);
+ *   env B200_ENGINE_COALESCE_US     = request-coalescing window in microseconds (default 0, or 200 when "dynamic_batching": true);
+ *   env B200_ENGINE_MIN_SHARD       = smallest per-GPU shard of a split request (default 32);
+ *   env B200_ENGINE_STAGE_PAGEABLE  = 0 disables the pinned staging of pageable request buffers; B200_ENGINE_STAGING_MB caps the pool (2048);
+ *   env B200_ENGINE_CHAIN / B200_ENGINE_CHAIN_MIN_BATCH = device-side serialisation of big forwards across instances (default on, 64);
+ *   env B200_ENGINE_PIPELINE_CHUNK  = sub-batch of the H2D/forward pipeline of a lone request (default 128, 0 = off).
+ * Kernel selection (debug / A-B measurements): B200_ENGINE_GRAPHS=0, B200_ENGINE_DENSEFUSE=0, B200_ENGINE_TILEFUSE=1 (opt-in fused
+ *   dense-layer tile kernel), B200_ENGINE_SPLIT_TRANSITION=0, B200_ENGINE_RESB=0.
  */
 #ifndef B200_ENGINE_H
 #define B200_ENGINE_H
