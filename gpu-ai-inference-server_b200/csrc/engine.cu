@@ -253,6 +253,19 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
     }
     if (weights_of_) BorrowDenseRuns(*weights_of_);
     else BuildDenseRuns();
+    // fp32 reference mode: scratch for the deterministic split-K of the SIMT convolutions at small batch
+    {
+        bool any_simt = false;
+        for (size_t i = 0; i < P.steps.size(); ++i) any_simt = any_simt || (P.steps[i].kind == StepKind::Conv && !prepared_[i].use_umma);
+        const char* e = getenv("B200_ENGINE_SPLITK");
+        if (any_simt && !(e && e[0] == '0')) {
+            splitk_bytes_ = (8u << 20) + 4096 * sizeof(unsigned int);
+            CudaCheck(cudaMalloc(&splitk_scratch_, splitk_bytes_), "cudaMalloc(split-K scratch)");
+            CudaCheck(cudaMemsetAsync(splitk_scratch_, 0, splitk_bytes_, stream_), "cudaMemset(split-K scratch)");
+            allocations_.push_back(splitk_scratch_);
+            device_bytes_ += splitk_bytes_;
+        }
+    }
     // Wide transition layers (Cout > 128): conv1x1_tma redoes the pooled transform of the A tile for every 128-column N tile;
     // materialising sum_2x2 relu(bn(x)) once and running a plain 1x1 conv over it is cheaper (kernels_poolbn.cu).
     {
@@ -462,6 +475,8 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
             a.out = vout;
             a.n = n;
             a.in_u8_hwc = u8;
+            a.splitk_scratch = splitk_scratch_;
+            a.splitk_bytes = splitk_bytes_;
             if (pr0.split_pool) {
                 kernels::View src = vin;
                 src.C = s.Cin;

@@ -140,6 +140,8 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     char* arena_ = nullptr;
     void* flush_buf_ = nullptr;
+    void* splitk_scratch_ = nullptr;  // fp32 SIMT split-K: tile counters + partial sums (small batches)
+    size_t splitk_bytes_ = 0;
     void* pool_scratch_ = nullptr;  // [max_batch][Ho][Wo][Cin] of the widest split transition
     size_t flush_bytes_ = 0;
     std::vector<void*> allocations_;

@@ -34,6 +34,8 @@ struct ConvArgs {
     const float* bias = nullptr;  // [Cout]
     bool post_relu = false;
     bool pool2 = false;  // A rows are 2x2 averages of (prologue-transformed) input pixels
+    void* splitk_scratch = nullptr;  // fp32 SIMT path: partial sums + tile counters for split-K on small batches (optional)
+    size_t splitk_bytes = 0;
     float out_mul = 1.f; // extra factor on the per-channel output scale (0.25 when the caller pooled the A operand itself)
     bool stem_nchw = false;  // `in` is the caller's fp32 NCHW image batch (7x7/s2/p3 stem, see kernels_stem.cu)
     const uint8_t* in_u8_hwc = nullptr;  // stem_nchw only: read raw uint8 [n][H][W][C] pixels instead (value / 255)

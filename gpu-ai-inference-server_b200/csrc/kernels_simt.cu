@@ -375,6 +375,10 @@ struct ConvP {
     int R, S, stride, pad;
     int M, K;
     int vecA, vecB, vecC;
+    // split-K (v2 kernel, small M): blockIdx.z = K slice; partial[z][m][n]; the LAST slice of a tile to finish sums them in z order
+    int splits, k_per_split;
+    float* partial;
+    unsigned int* counters;
 };
 
 template <int BM, int BN, int BK, int TM, int TN>
@@ -540,13 +544,15 @@ __global__ void __launch_bounds__(256) conv_simt_f32_v2_kernel(ConvP p) {
     }
     const int b_kk = tid / (BN / 4), b_nq = (tid % (BN / 4)) * 4;
     const bool b_thread = !kBHalf || tid < BK * (BN / 4);
+    const int k_begin = p.splits > 1 ? (int)blockIdx.z * p.k_per_split : 0;
+    const int k_end = p.splits > 1 ? (k_begin + p.k_per_split < p.K ? k_begin + p.k_per_split : p.K) : p.K;
     float4 ra[kASlots], rb;
     auto fetch = [&](int k0) {
         const int k = k0 + a_kq;
         const int c = k % p.Cin, rs = k / p.Cin;
         const int s = rs % p.S, r = rs / p.S;
         float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.pre_scale && k < p.K) {
+        if (p.pre_scale && k < k_end) {
             sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + c));
             sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + c));
         }
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(256) conv_simt_f32_v2_kernel(ConvP p) {
         for (int i = 0; i < kASlots; ++i) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             const int ih = a_ih0[i] + r, iw = a_iw0[i] + s;
-            if (a_ok[i] && k < p.K && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
+            if (a_ok[i] && k < k_end && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W) {
                 v = __ldg(reinterpret_cast<const float4*>(p.in + (a_base[i] + (size_t)ih * p.W + iw) * p.in_pitch + p.in_coff + c));
                 if (p.pre_scale) {
                     v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
@@ -566,7 +572,7 @@ __global__ void __launch_bounds__(256) conv_simt_f32_v2_kernel(ConvP p) {
         }
         rb = make_float4(0.f, 0.f, 0.f, 0.f);
         const int kb = k0 + b_kk, nn = n0 + b_nq;
-        if (b_thread && kb < p.K && nn < p.Cout) rb = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)kb * p.Cout + nn));
+        if (b_thread && kb < k_end && nn < p.Cout) rb = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)kb * p.Cout + nn));
     };
 
     float acc[TM][TN];
@@ -575,8 +581,8 @@ __global__ void __launch_bounds__(256) conv_simt_f32_v2_kernel(ConvP p) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    fetch(0);
-    for (int k0 = 0; k0 < p.K; k0 += BK) {
+    fetch(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
 #pragma unroll
         for (int i = 0; i < kASlots; ++i) {
             if (!kAHalf || tid < BM * 4) {
@@ -586,7 +592,7 @@ __global__ void __launch_bounds__(256) conv_simt_f32_v2_kernel(ConvP p) {
         }
         if (b_thread) *reinterpret_cast<float4*>(&Bs[b_kk][b_nq]) = rb;
         __syncthreads();
-        if (k0 + BK < p.K) fetch(k0 + BK);
+        if (k0 + BK < k_end) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];
@@ -603,6 +609,42 @@ __global__ void __launch_bounds__(256) conv_simt_f32_v2_kernel(ConvP p) {
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
+    }
+    if (p.splits > 1) {
+        // Deterministic split-K: every K slice parks its partial tile, the slice that arrives last adds them up in slice order
+        // (so the result does not depend on which one that is) and runs the epilogue.
+        const size_t zstride = (size_t)p.M * p.Cout;
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int m = m0 + ty * TM + i;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int nn = n0 + tx * TN + j;
+                if (nn < p.Cout) __stcg(p.partial + (size_t)blockIdx.z * zstride + (size_t)m * p.Cout + nn, acc[i][j]);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        __shared__ unsigned int s_last;
+        const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        if (tid == 0) s_last = atomicAdd(&p.counters[tile], 1u) == (unsigned int)(p.splits - 1) ? 1u : 0u;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int m = m0 + ty * TM + i;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int nn = n0 + tx * TN + j;
+                float t = 0.f;
+                if (m < p.M && nn < p.Cout)
+                    for (int z = 0; z < p.splits; ++z) t += __ldcg(p.partial + (size_t)z * zstride + (size_t)m * p.Cout + nn);
+                acc[i][j] = t;
+            }
+        }
+        if (tid == 0) p.counters[tile] = 0u;  // ready for the next launch (launches on a stream are serialised)
     }
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
@@ -785,6 +827,7 @@ cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t strea
     p.Ho = a.out.H; p.Wo = a.out.W; p.Cout = a.Cout; p.out_pitch = a.out.pitch; p.out_coff = a.out.c_off;
     p.R = a.R; p.S = a.S; p.stride = a.stride; p.pad = a.pad;
     p.M = a.n * p.Ho * p.Wo; p.K = a.R * a.S * a.Cin;
+    p.splits = 1; p.k_per_split = p.K; p.partial = nullptr; p.counters = nullptr;
     p.vecA = (a.Cin % 4 == 0 && a.in.pitch % 4 == 0 && a.in.c_off % 4 == 0 && ((uintptr_t)p.in % 16) == 0 &&
               (!a.pre_scale || (((uintptr_t)a.pre_scale % 16) == 0 && ((uintptr_t)a.pre_shift % 16) == 0)));
     p.vecB = (a.Cout % 4 == 0 && ((uintptr_t)w_kn % 16) == 0);
@@ -807,13 +850,34 @@ cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t strea
         const int bn = narrow ? 32 : 64;
         const int ntile = (a.Cout + bn - 1) / bn;
         auto ctas = [&](int bm) { return ((p.M + bm - 1) / bm) * ntile; };
+        // Small batches leave most SMs without a tile and every tile with a long serial K loop (batch 1, 3x3 conv of a 7x7 image:
+        // ONE CTA walks K = 1152): cut K into slices across blockIdx.z until ~2 CTAs per SM exist.
+        const int bm_small = narrow ? 64 : 32;
+        unsigned int gz = 1;
+        if (a.splitk_scratch && ctas(bm_small) < sms) {
+            const int tiles = ctas(bm_small);
+            int want = (2 * sms + tiles - 1) / tiles;
+            const int max_by_k = p.K / 64;  // at least four 16-step slabs per slice
+            if (want > max_by_k) want = max_by_k;
+            if (want > 16) want = 16;
+            const size_t counters_bytes = 4096 * sizeof(unsigned int);
+            while (want > 1 && (size_t)want * p.M * p.Cout * sizeof(float) + counters_bytes > a.splitk_bytes) --want;
+            if (want > 1 && tiles <= 4096) {
+                p.k_per_split = ((p.K + want - 1) / want + 15) / 16 * 16;
+                p.splits = (p.K + p.k_per_split - 1) / p.k_per_split;
+                p.counters = reinterpret_cast<unsigned int*>(a.splitk_scratch);
+                p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(a.splitk_scratch) + counters_bytes);
+                gz = (unsigned int)p.splits;
+                if (gz <= 1) { p.splits = 1; gz = 1; }
+            }
+        }
         if (narrow) {
             if (ctas(128) >= 2 * sms) conv_simt_f32_v2_kernel<128, 32, 4, 4><<<dim3((p.M + 127) / 128, ntile), 256, 0, stream>>>(p);
-            else conv_simt_f32_v2_kernel<64, 32, 2, 4><<<dim3((p.M + 63) / 64, ntile), 256, 0, stream>>>(p);
+            else conv_simt_f32_v2_kernel<64, 32, 2, 4><<<dim3((p.M + 63) / 64, ntile, gz), 256, 0, stream>>>(p);
         } else {
             if (ctas(128) >= 2 * sms) conv_simt_f32_v2_kernel<128, 64, 8, 4><<<dim3((p.M + 127) / 128, ntile), 256, 0, stream>>>(p);
             else if (ctas(64) >= sms) conv_simt_f32_v2_kernel<64, 64, 4, 4><<<dim3((p.M + 63) / 64, ntile), 256, 0, stream>>>(p);
-            else conv_simt_f32_v2_kernel<32, 64, 2, 4><<<dim3((p.M + 31) / 32, ntile), 256, 0, stream>>>(p);
+            else conv_simt_f32_v2_kernel<32, 64, 2, 4><<<dim3((p.M + 31) / 32, ntile, gz), 256, 0, stream>>>(p);
         }
     } else if (a.Cout <= 32) {
         constexpr int BM = 128, BN = 32;
