@@ -37,6 +37,16 @@ def test_small_batches_round_robin_over_replicas(pkg):
     assert pkg.plan_shards(256, 8) == [(g, 32 * g, 32) for g in range(8)]
 
 
+def test_default_min_shard_keeps_mid_size_requests_on_few_gpus(pkg):
+    """Engine default (B200_ENGINE_MIN_SHARD = 32): a request is only cut into shards of >= 32 samples, so under mixed concurrent
+    traffic a 64-image request occupies two GPUs, not eight, and anything below 64 goes whole to one GPU (round-robin)."""
+    assert pkg.plan_shards(64, 8, 256, 32, 0) == [(0, 0, 32), (1, 32, 32)]
+    assert pkg.plan_shards(128, 8, 256, 32, 0) == [(g, 32 * g, 32) for g in range(4)]
+    assert pkg.plan_shards(256, 8, 256, 32, 0) == [(g, 32 * g, 32) for g in range(8)]
+    assert pkg.plan_shards(63, 8, 256, 32, 5) == [(5, 0, 63)]
+    assert pkg.plan_shards(100, 2, 256, 32, 0) == [(0, 0, 50), (1, 50, 50)]
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, {root!r})
