@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kPbThreads) pool_bn_relu_2x2_kernel(const PbPa
     using ME = MmaElem<MmaT>;
     constexpr int EPV = ME::kPerVec;
     constexpr int kPairs = EPV / 2;
-    __shared__ uint32_t s_sc[kPbMaxCin / 2], s_sh[kPbMaxCin / 2];
+    __shared__ __align__(16) uint32_t s_sc[kPbMaxCin / 2], s_sh[kPbMaxCin / 2];
     for (int i = threadIdx.x; i < (p.Cin + 1) / 2; i += kPbThreads) {
         const int c0 = 2 * i, c1 = 2 * i + 1;
         s_sc[i] = PackPair<MmaT>(p.scale[c0], c1 < p.Cin ? p.scale[c1] : 0.f);
@@ -60,9 +60,11 @@ __global__ void __launch_bounds__(kPbThreads) pool_bn_relu_2x2_kernel(const PbPa
         q[3] = LdgNc(src + row_b + p.in_pitch_b);
         uint32_t sc[kPairs], sh[kPairs];
 #pragma unroll
-        for (int e = 0; e < kPairs; ++e) {
-            sc[e] = s_sc[piece * kPairs + e];
-            sh[e] = s_sh[piece * kPairs + e];
+        for (int e = 0; e < kPairs; e += 4) {  // 16-byte shared loads (word loads at this stride were 4-way bank conflicted)
+            const uint4 a = *reinterpret_cast<const uint4*>(&s_sc[piece * kPairs + e]);
+            const uint4 b = *reinterpret_cast<const uint4*>(&s_sh[piece * kPairs + e]);
+            sc[e] = a.x; sc[e + 1] = a.y; sc[e + 2] = a.z; sc[e + 3] = a.w;
+            sh[e] = b.x; sh[e + 1] = b.y; sh[e + 2] = b.z; sh[e + 3] = b.w;
         }
         const uint4 v = p.relu ? PoolPiece<MmaT, true>(q, sc, sh) : PoolPiece<MmaT, false>(q, sc, sh);
         *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.out_pitch_b + p.out_coff_b + piece * 16) = v;
