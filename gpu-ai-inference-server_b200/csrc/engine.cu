@@ -266,16 +266,21 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
             device_bytes_ += splitk_bytes_;
         }
     }
-    // Wide transition layers (Cout > 128): conv1x1_tma redoes the pooled transform of the A tile for every 128-column N tile;
+    // Transition layers: conv1x1_tma<POOL> redoes the pooled transform of the A tile for every 128-column N tile (Cout 256 / 512);
     // materialising sum_2x2 relu(bn(x)) once and running a plain 1x1 conv over it is cheaper (kernels_poolbn.cu).
     {
         const char* e = getenv("B200_ENGINE_SPLIT_TRANSITION");
         const bool enabled = !(e && e[0] == '0');
+        // "1": only the wide ones (Cout > 128).  Default: transition 1 (one N tile) as well - the fused kernel's pooled transform
+        // reads four planes through 8 warps and streams at 2.8 TB/s; the memory-bound pass + plain conv is 73 -> 60 us.
+        const int min_cout = (e && e[0] == '1') ? 128 : 0;
         size_t need = 0;
         for (size_t i = 0; enabled && i < P.steps.size(); ++i) {
             const Step& s = P.steps[i];
             Prepared& pr = prepared_[i];
-            if (s.kind != StepKind::Conv || !s.pool2_fused || !pr.use_umma || s.Cout <= 128 || pr.fused_run >= 0) continue;
+            if (s.kind != StepKind::Conv || !s.pool2_fused || !pr.use_umma || pr.fused_run >= 0) continue;
+            // single-N-tile transitions only pay off in e4m3 (bf16 doubles the bytes of the extra round trip: 3.60 -> 3.62 ms)
+            if (s.Cout <= (pr.in.dtype == DType::FP8 ? min_cout : 128)) continue;
             kernels::View vin = pr.in;
             vin.C = s.Cin;
             kernels::View pooled = vin;

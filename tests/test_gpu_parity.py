@@ -428,7 +428,7 @@ def test_split_wide_transitions_are_bit_identical(pkg, repo_dir, monkeypatch, pr
     monkeypatch.setenv("B200_ENGINE_INSTANCES", "1")
     x = synth.to_model_input(synth.synthetic_images_u8(6, start=4400))
     outs, launches = {}, {}
-    for flag in ("0", "1"):
+    for flag in ("0", "1", "2"):   # off / wide transitions only / all three (the default)
         monkeypatch.setenv("B200_ENGINE_SPLIT_TRANSITION", flag)
         mgr = pkg.InferenceManager(repo_dir)
         try:
@@ -439,7 +439,9 @@ def test_split_wide_transitions_are_bit_identical(pkg, repo_dir, monkeypatch, pr
             launches[flag] = pkg.kernel_launch_count() - n0
         finally:
             mgr.shutdown()
-    assert launches["1"] == launches["0"] + 2, launches   # two transitions gained a kernel each
+    assert launches["2"] == launches["0"] + (3 if precision == "fp8" else 2), launches
+    assert np.array_equal(outs["0"], outs["2"])
+    assert launches["1"] == launches["0"] + 2, launches   # "1": the two wide transitions gained a kernel each
     assert np.array_equal(outs["0"], outs["1"])
 
 
