@@ -177,10 +177,53 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         const std::vector<float>& w = P.consts[s.weight].data;  // [Cout][R][S][Cin]
         const int K = s.R * s.S * s.Cin;
         pr.use_umma = s.stem_nchw || pr.in.dtype != DType::F32;
+        // FP32 mode: tcgen05 with bf16-split operands (kernels_f32x3.cu) wherever the shape allows; B200_ENGINE_FP32_EXACT=1 keeps
+        // every convolution on the exact FFMA kernels
+        const char* exact_env = getenv("B200_ENGINE_FP32_EXACT");
+        const bool f32x3_enabled = !(exact_env && exact_env[0] == '1');
+        pr.use_f32x3 = !pr.use_umma && f32x3_enabled && kernels::ConvF32x3Supported(a);
         if (weights_of_) {  // same plan, same device: the lender's packed weights, scales and tensor map serve this instance too
             const Prepared& lp = weights_of_->prepared_[i];
             pr.w_kn = lp.w_kn;
             pr.umma = lp.umma;
+            continue;
+        }
+        if (pr.use_f32x3) {
+            // [Cout_pad][R*S*Cin*2] bf16: per filter tap and 32 input channels one 128-byte row [w0 x32 | w1 x32], w = w0 + w1
+            const int bn = kernels::F32x3TileN(a);
+            const int cout_pad = (s.Cout + bn - 1) / bn * bn;
+            const int K_pad = K * 2;
+            std::vector<uint16_t> packed((size_t)cout_pad * K_pad, 0);
+            for (int o = 0; o < s.Cout; ++o)
+                for (int tap = 0; tap < s.R * s.S; ++tap)
+                    for (int c = 0; c < s.Cin; ++c) {
+                        const float v = w[((size_t)o * s.R * s.S + tap) * s.Cin + c];
+                        const uint16_t h0 = F32ToBf16(v);
+                        const uint32_t u0 = (uint32_t)h0 << 16;
+                        float f0;
+                        memcpy(&f0, &u0, 4);
+                        const size_t idx = (size_t)o * K_pad + kernels::F32x3WeightIndex(tap, c, s.Cin);
+                        packed[idx] = h0;
+                        packed[idx + 32] = F32ToBf16(v - f0);
+                    }
+            std::vector<float> ones(s.Cout, 1.f);
+            pr.umma.w = Upload(packed.data(), packed.size() * 2);
+            pr.umma.out_scale = (const float*)Upload(ones.data(), ones.size() * 4);
+            pr.umma.K_pad = K_pad;
+            pr.umma.Cout_pad = cout_pad;
+            CUtensorMap* tm = new CUtensorMap;
+            cuuint64_t dims[2] = {(cuuint64_t)K_pad, (cuuint64_t)cout_pad};
+            cuuint64_t strides[1] = {(cuuint64_t)K_pad * 2};
+            cuuint32_t box[2] = {64u, (cuuint32_t)bn};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = GetEncodeTiled()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(pr.umma.w), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                delete tm;
+                throw CudaError("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for conv '" + s.name + "'");
+            }
+            pr.umma.tensor_map = tm;
             continue;
         }
         if (!pr.use_umma) {
@@ -256,7 +299,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
     // fp32 reference mode: scratch for the deterministic split-K of the SIMT convolutions at small batch
     {
         bool any_simt = false;
-        for (size_t i = 0; i < P.steps.size(); ++i) any_simt = any_simt || (P.steps[i].kind == StepKind::Conv && !prepared_[i].use_umma);
+        for (size_t i = 0; i < P.steps.size(); ++i) any_simt = any_simt || (P.steps[i].kind == StepKind::Conv && !prepared_[i].use_umma && !prepared_[i].use_f32x3);
         const char* e = getenv("B200_ENGINE_SPLITK");
         if (any_simt && !(e && e[0] == '0')) {
             splitk_bytes_ = (8u << 20) + 4096 * sizeof(unsigned int);
@@ -496,7 +539,9 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
                 e = kernels::Conv1x1Tma(a, pr0.umma, stream_);
                 break;
             }
-            e = pr0.use_umma ? kernels::ConvUmma(a, pr0.umma, stream_) : kernels::ConvSimtF32(a, pr0.w_kn, stream_);
+            e = pr0.use_umma ? kernels::ConvUmma(a, pr0.umma, stream_)
+                : pr0.use_f32x3 ? kernels::ConvF32x3(a, pr0.umma, stream_)
+                                : kernels::ConvSimtF32(a, pr0.w_kn, stream_);
             break;
         }
         case StepKind::MaxPool: e = kernels::MaxPool(vin, vout, n, s.R, s.stride, s.pad, stream_); break;
@@ -767,7 +812,7 @@ std::string Replica::ProfileSteps(int n, int repeats) {
         os << "{\"step\":" << i << ",\"kind\":\"" << StepKindName(s.kind) << "\",\"name\":\"";
         for (char c : s.name) os << ((c == '"' || c == '\\') ? '_' : c);
         os << "\",\"ms\":" << ms[i] / repeats << ",\"flops\":" << s.flops * n << ",\"bytes\":" << s.bytes * n
-           << ",\"umma\":" << (prepared_[i].use_umma ? "true" : "false");
+           << ",\"umma\":" << ((prepared_[i].use_umma || prepared_[i].use_f32x3) ? "true" : "false");
         if (s.kind == StepKind::Conv)
             os << ",\"Cin\":" << s.Cin << ",\"Cout\":" << s.Cout << ",\"R\":" << s.R << ",\"H\":" << P.tensors[s.out].H;
         os << "}";

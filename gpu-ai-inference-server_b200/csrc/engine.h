@@ -100,6 +100,7 @@ private:
         const float* w_kn = nullptr;   // SIMT weights
         kernels::UmmaWeights umma;     // tcgen05 weights
         bool use_umma = false;
+        bool use_f32x3 = false;        // FP32 mode on tcgen05: bf16-split operands (kernels_f32x3.cu); weights live in `umma`
         kernels::View in, in2, out;
         const float* scale = nullptr;
         const float* shift = nullptr;

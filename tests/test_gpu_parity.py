@@ -70,7 +70,8 @@ def _conv_node(x, w, out, k, s=1, p=0, bias=None):
 
 CASES = ["conv1x1_bn_relu", "conv1x1_partial_chunk", "conv1x1_ktail", "conv1x1_long", "conv3x3", "stem_maxpool", "transition",
          "transition_wide", "dense_block", "dense_block_copy", "dense_block7", "cout256", "gap_gemm_softmax"]
-TOL = {"fp32": 2e-5, "bf16": 2.5e-2, "fp8": 1.5e-1}
+# "fp32": FP32 mode = tcgen05 with bf16-split operands (three MMAs per product, ~2^-17 per term); "fp32-exact": the FFMA kernels
+TOL = {"fp32": 1e-4, "fp32-exact": 2e-5, "bf16": 2.5e-2, "fp8": 1.5e-1}
 
 
 def _build_case(case, tmp_path, rng):
@@ -154,15 +155,17 @@ def _build_case(case, tmp_path, rng):
     return path, case, shp, out
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp8"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32-exact", "bf16", "fp8"])
 @pytest.mark.parametrize("case", CASES)
 def test_operator_graphs_match_oracle(pkg, tmp_path, monkeypatch, case, precision):
+    if precision == "fp32-exact":
+        monkeypatch.setenv("B200_ENGINE_FP32_EXACT", "1")
     rng = np.random.default_rng(abs(hash(case)) % 2**31)
     path, name, shp, out = _build_case(case, tmp_path, rng)
     n = 5
     x = rng.uniform(0, 1, (n,) + tuple(shp)).astype(np.float32) if shp[0] == 3 else rng.normal(0, 1, (n,) + tuple(shp)).astype(np.float32)
     want = OnnxOracle(path).run({"x": x})[0]
-    got = _serve(pkg, str(tmp_path), name, {"x": x}, {"y": (n,) + tuple(out)}, precision, monkeypatch)[0]
+    got = _serve(pkg, str(tmp_path), name, {"x": x}, {"y": (n,) + tuple(out)}, precision.split("-")[0], monkeypatch)[0]
     assert got.shape == want.shape
     err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-6)
     assert np.isfinite(got).all() and err < TOL[precision], f"{case}/{precision}: rel err {err:.3e}"
@@ -197,8 +200,12 @@ def test_densenet_fp32_matches_golden_logits(pkg, repo_dir, monkeypatch):
     x = synth.to_model_input(synth.synthetic_images_u8(n, start=int(g["start"])))
     got = _serve(pkg, repo_dir, "densenet_onnx", {"data_0": x}, {"fc6_1": (n, 1000)}, "fp32", monkeypatch)[0]
     a = _agreement(g["logits_fp64"], got)
+    print("fp32 (tcgen05, bf16-split operands) vs fp64 golden:", a)
     assert a["max_rel"] < 1e-3 and a["top1"] == 1.0, a          # north_star fp32 gate
-    assert _agreement(g["logits_fp32"], got)["max_rel"] < 1e-4   # in practice fp32-reassociation noise only
+    assert a["max_rel"] < 2e-4, a                                # what three bf16 products per term deliver (simulated 4e-5)
+    monkeypatch.setenv("B200_ENGINE_FP32_EXACT", "1")            # the exact FFMA kernels: fp32-reassociation noise only
+    exact = _serve(pkg, repo_dir, "densenet_onnx", {"data_0": x}, {"fc6_1": (n, 1000)}, "fp32", monkeypatch)[0]
+    assert _agreement(g["logits_fp32"], exact)["max_rel"] < 1e-4
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp8"])

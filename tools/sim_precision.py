@@ -20,7 +20,7 @@ class Sim:
         self.m = onnx_lite.load(path); self.mode = mode; self.store = store
         self.calib = {}  # tensor name -> amax
     def qstore(self, x, name):
-        if self.mode == "fp32" or self.mode=="tf32": return x
+        if self.mode in ("fp32", "tf32", "bf16x3"): return x
         if self.store == "bf16" or self.mode == "bf16": return q_bf16(x)
         amax = float(x.abs().max()); s = E4M3_MAX / max(amax, 1e-12) / 2
         return q_fp8(x, s)
@@ -46,6 +46,14 @@ class Sim:
         with torch.no_grad():
             for n in g.nodes:
                 a = n.attrs; xs = [env[i] for i in n.inputs]; op = n.op_type
+                if op == "Conv" and self.mode == "bf16x3":
+                    # fp32 emulated on bf16 tensor cores: a = a0 + a1, w = w0 + w1 (bf16 each); a0*w0 + a0*w1 + a1*w0, fp32 accumulate
+                    a0 = q_bf16(xs[0]); a1 = q_bf16(xs[0] - a0)
+                    w0 = q_bf16(xs[1]); w1 = q_bf16(xs[1] - w0)
+                    kw = dict(stride=a["strides"], padding=a["pads"][:2])
+                    y = F.conv2d(a1, w0, None, **kw) + F.conv2d(a0, w1, None, **kw) + F.conv2d(a0, w0, xs[2] if len(xs) > 2 else None, **kw)
+                    env[n.outputs[0]] = y
+                    continue
                 if op == "Conv":
                     inp = self.qact(xs[0], n.inputs[0])
                     w = self.qw(xs[1])
@@ -86,7 +94,8 @@ if __name__ == "__main__":
     x = synth.to_model_input(synth.synthetic_images_u8(N, start=200))
     ref = Sim(path, "fp32").run(x)
     top5 = np.argsort(-ref, 1)[:, :5]
-    for mode, store in [("tf32", "fp32"), ("bf16", "bf16"), ("fp8", "bf16"), ("fp8", "fp8")]:
+    modes = [("bf16x3", "fp32")] if len(sys.argv) > 2 and sys.argv[2] == "x3" else None
+    for mode, store in modes or [("tf32", "fp32"), ("bf16", "bf16"), ("fp8", "bf16"), ("fp8", "fp8")]:
         t = time.time(); y = Sim(path, mode, store).run(x)
         t5 = np.argsort(-y, 1)[:, :5]
         agree_set = np.mean([len(set(a) & set(b)) / 5 for a, b in zip(top5, t5)])
