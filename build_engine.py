@@ -79,15 +79,25 @@ def build_tools(quiet: bool = False) -> str:
     """The native load generator (tools/rest_replay.cpp): links against nothing but the C-ABI of the library."""
     out = os.path.join(ROOT, "build", "rest_replay")
     src = os.path.join(ROOT, "tools", "rest_replay.cpp")
-    if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
-        return out
-    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-I", INC, src, "-o", out, "-L", os.path.dirname(LIB), "-linference_engine",
-           "-Wl,-rpath,$ORIGIN/../gpu-ai-inference-server_b200/lib"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"rest_replay build failed:\n{r.stdout}\n{r.stderr}")
-    if not quiet:
-        print(f"[build] {out}")
+    if not (os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(LIB))):
+        cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-I", INC, src, "-o", out, "-L", os.path.dirname(LIB), "-linference_engine",
+               "-Wl,-rpath,$ORIGIN/../gpu-ai-inference-server_b200/lib"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"rest_replay build failed:\n{r.stdout}\n{r.stderr}")
+        if not quiet:
+            print(f"[build] {out}")
+    # run-time test program of the C++ API (inference::Tensor, inference::InferenceManager)
+    api = os.path.join(ROOT, "build", "api_test")
+    api_src = os.path.join(ROOT, "tests", "cpp", "api_test.cpp")
+    if not (os.path.exists(api) and os.path.getmtime(api) > max(os.path.getmtime(api_src), os.path.getmtime(LIB))):
+        cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-I", INC, api_src, "-o", api, "-L", os.path.dirname(LIB), "-linference_engine",
+               "-Wl,-rpath,$ORIGIN/../gpu-ai-inference-server_b200/lib"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"api_test build failed:\n{r.stdout}\n{r.stderr}")
+        if not quiet:
+            print(f"[build] {api}")
     return out
 
 

@@ -244,7 +244,10 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         const bool stem = s.Cin < 16;
         // stem packing: k = r*32 + s*4 + c (8 pixels x 4 channels per filter row, zero padded); the fused NCHW stem
         // starts its 8-pixel window one pixel further left (16-byte aligned rows), so its taps sit at s+1
-        const int K_pad = stem ? ((s.R * 32 + kc - 1) / kc * kc) : s.R * s.S * cin_pad;
+        // FP32 mode stem: w = w0 + w1, the residual tile follows the leading tile along K (kernels_stem.cu, SPLIT)
+        const bool stem_split = s.stem_nchw && pr.out.dtype == DType::F32;
+        const int K_stem = (s.R * 32 + kc - 1) / kc * kc;
+        const int K_pad = stem ? (stem_split ? 2 : 1) * K_stem : s.R * s.S * cin_pad;
         const int bn = s.stem_nchw ? 64 : s.Cout <= 32 ? 32 : s.Cout <= 64 ? 64 : 128;
         const int cout_pad = (s.Cout + bn - 1) / bn * bn;
         std::vector<float> scale(s.Cout, 1.f);
@@ -273,6 +276,12 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
                         float v = w[(((size_t)o * s.R + r) * s.S + ss) * s.Cin + c];
                         int kk = stem ? r * 32 + (ss + (s.stem_nchw ? 1 : 0)) * 4 + c : (r * s.S + ss) * cin_pad + c;
                         put(o, kk, v);
+                        if (stem_split) {
+                            const uint32_t u0 = (uint32_t)F32ToBf16(v) << 16;
+                            float f0;
+                            memcpy(&f0, &u0, 4);
+                            put(o, K_stem + kk, v - f0);
+                        }
                     }
         pr.umma.w = Upload(packed.data(), packed.size());
         pr.umma.out_scale = (const float*)Upload(scale.data(), scale.size() * 4);

@@ -51,6 +51,7 @@ struct SParams {
     int plane1_off;      // byte offset of the odd-row plane inside a buffer
     int buf_bytes;
     int tiles_per_strip;
+    int lo_off;          // SPLIT (fp32 mode): byte offset of the residual-term planes inside a buffer
 };
 
 __device__ __forceinline__ uint32_t PackBf16(float a, float b) {
@@ -58,12 +59,21 @@ __device__ __forceinline__ uint32_t PackBf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <typename OutT>
+// fp32 -> leading bf16 term (returned packed with its neighbour) and residual term, see kernels_f32x3.cu
+__device__ __forceinline__ void SplitPackBf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = PackBf16(a, b);
+    lo = PackBf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+}
+
+// SPLIT = FP32 mode (OutT = float): every pixel is stored twice, as its leading bf16 terms and as the bf16 residuals
+// (x = x0 + x1), the weights likewise (w = w0 + w1, two resident tiles), and each tile runs x1*w0 + x0*w1 + x0*w0.
+template <typename OutT, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_constant__ CUtensorMap tmap_w, const SParams p) {
+    constexpr int kWSets = SPLIT ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_w = smem;
-    uint8_t* s_buf = smem + kStemWBytes;
+    uint8_t* s_buf = smem + kWSets * kStemWBytes;
     float* s_out_scale = reinterpret_cast<float*>(s_buf + 2 * p.buf_bytes);
     float* s_bias = s_out_scale + kStemN;
     uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_bias + kStemN);
@@ -162,6 +172,18 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (!dst[u]) continue;
+                    if (SPLIT) {
+                        uint32_t h[8], l[8];
+                        SplitPackBf16(c[u][0].x, c[u][1].x, h[0], l[0]); SplitPackBf16(c[u][2].x, 0.f, h[1], l[1]);
+                        SplitPackBf16(c[u][0].y, c[u][1].y, h[2], l[2]); SplitPackBf16(c[u][2].y, 0.f, h[3], l[3]);
+                        SplitPackBf16(c[u][0].z, c[u][1].z, h[4], l[4]); SplitPackBf16(c[u][2].z, 0.f, h[5], l[5]);
+                        SplitPackBf16(c[u][0].w, c[u][1].w, h[6], l[6]); SplitPackBf16(c[u][2].w, 0.f, h[7], l[7]);
+                        StsV4(dst[u], make_uint4(h[0], h[1], h[2], h[3]));
+                        StsV4(dst[u] + 16, make_uint4(h[4], h[5], h[6], h[7]));
+                        StsV4(dst[u] + p.lo_off, make_uint4(l[0], l[1], l[2], l[3]));
+                        StsV4(dst[u] + p.lo_off + 16, make_uint4(l[4], l[5], l[6], l[7]));
+                        continue;
+                    }
                     StsV4(dst[u], make_uint4(PackBf16(c[u][0].x, c[u][1].x), PackBf16(c[u][2].x, 0.f),
                                              PackBf16(c[u][0].y, c[u][1].y), PackBf16(c[u][2].y, 0.f)));
                     StsV4(dst[u] + 16, make_uint4(PackBf16(c[u][0].z, c[u][1].z), PackBf16(c[u][2].z, 0.f),
@@ -196,14 +218,29 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
                 __syncwarp();
                 if (lane == 0) MbarArrive(&tmem_empty[acc]);
                 if (valid) {
-                    constexpr int kWords = 32 * (int)sizeof(OutT) / 4;
-                    uint32_t w[kWords];
-                    if (p.post_relu) EpiloguePack32Smem<OutT, true>(r, sc_addr, bi_addr, w);
-                    else EpiloguePack32Smem<OutT, false>(r, sc_addr, bi_addr, w);
-                    constexpr int kPer = 16 / (int)sizeof(OutT);  // channels per 16-byte store
+                    if constexpr (SPLIT) {
 #pragma unroll
-                    for (int q = 0; q < kWords / 4; ++q)
-                        if (half * 32 + q * kPer < p.Cout) *reinterpret_cast<uint4*>(orow + q * kPer) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                        for (int q = 0; q < 8; ++q) {
+                            if (half * 32 + q * 4 >= p.Cout) continue;
+                            const float4 s4 = LdsF4(sc_addr + q * 16), b4 = LdsF4(bi_addr + q * 16);
+                            float4 v;
+                            v.x = fmaf(__uint_as_float(r[4 * q]), s4.x, b4.x);
+                            v.y = fmaf(__uint_as_float(r[4 * q + 1]), s4.y, b4.y);
+                            v.z = fmaf(__uint_as_float(r[4 * q + 2]), s4.z, b4.z);
+                            v.w = fmaf(__uint_as_float(r[4 * q + 3]), s4.w, b4.w);
+                            if (p.post_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4*>(orow + q * 4) = v;
+                        }
+                    } else {
+                        constexpr int kWords = 32 * (int)sizeof(OutT) / 4;
+                        uint32_t w[kWords];
+                        if (p.post_relu) EpiloguePack32Smem<OutT, true>(r, sc_addr, bi_addr, w);
+                        else EpiloguePack32Smem<OutT, false>(r, sc_addr, bi_addr, w);
+                        constexpr int kPer = 16 / (int)sizeof(OutT);  // channels per 16-byte store
+#pragma unroll
+                        for (int q = 0; q < kWords / 4; ++q)
+                            if (half * 32 + q * kPer < p.Cout) *reinterpret_cast<uint4*>(orow + q * kPer) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                    }
                 }
                 __syncwarp();
             }
@@ -211,8 +248,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
     } else if (warp == 12) {
         // =========================================================== weights: TMA once, resident
         if (ElectOne()) {
-            MbarArriveExpectTx(w_bar, (uint32_t)kStemWBytes);
-            for (int c = 0; c < kStemWChunks; ++c) TmaLoad2D(s_w + c * kStemN * 128, &tmap_w, w_bar, c * 64, 0);
+            MbarArriveExpectTx(w_bar, (uint32_t)(kWSets * kStemWBytes));
+            for (int c = 0; c < kWSets * kStemWChunks; ++c) TmaLoad2D(s_w + c * kStemN * 128, &tmap_w, w_bar, c * 64, 0);
         }
         __syncwarp();
     } else {
@@ -235,12 +272,18 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
                     const uint32_t d_addr = tmem_u + acc * kStemN;
                     const uint64_t a_tile = a_buf + (uint64_t)(tile * kTileM);  // 16 bytes per slot, address field is >>4
 #pragma unroll
-                    for (int r = 0; r < 7; ++r) {
-                        const uint32_t arow = (uint32_t)(((r & 1) * p.plane1_off + (r >> 1) * p.row_pitch) >> 4);
+                    for (int pass = SPLIT ? 0 : 2; pass < 3; ++pass) {  // SPLIT: x1*w0, x0*w1, x0*w0 (smallest terms first)
+                        const uint32_t a_set = pass == 0 ? (uint32_t)(p.lo_off >> 4) : 0u;
+                        const uint32_t b_set = pass == 1 ? (uint32_t)(kStemWBytes >> 4) : 0u;
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const uint32_t boff = (uint32_t)((r >> 1) * (kStemN * 128 / 16) + (r & 1) * 4 + ks * 2);
-                            UmmaSS<0>(d_addr, a_tile + (uint64_t)(arow + 2 * ks), b_base + (uint64_t)boff, idesc, (r | ks) ? 1u : 0u);
+                        for (int r = 0; r < 7; ++r) {
+                            const uint32_t arow = (uint32_t)(((r & 1) * p.plane1_off + (r >> 1) * p.row_pitch) >> 4) + a_set;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint32_t boff = (uint32_t)((r >> 1) * (kStemN * 128 / 16) + (r & 1) * 4 + ks * 2) + b_set;
+                                UmmaSS<0>(d_addr, a_tile + (uint64_t)(arow + 2 * ks), b_base + (uint64_t)boff, idesc,
+                                          (pass > (SPLIT ? 0 : 2) || r || ks) ? 1u : 0u);
+                            }
                         }
                     }
                     UmmaCommit(&tmem_full[acc]);
@@ -259,13 +302,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
 }
 
 // Strip height and buffer geometry; returns false when even T = 1 does not fit in shared memory.
-bool StemGeometry(int H, int W, SParams* p) {
+bool StemGeometry(int H, int W, SParams* p, bool split = false) {
     const int Ho = (H + 2 * 3 - 7) / 2 + 1, Wo = (W + 2 * 3 - 7) / 2 + 1;
     const int P = (W + 8) * 8;
     for (int T = Ho < 16 ? Ho : 16; T >= 1; --T) {
         const int rows0 = T + 3, rows1 = T + 2;  // even / odd plane rows of a (2T+5)-row strip
-        const int buf = ((rows0 + rows1) * P + kStemSlack + 127) / 128 * 128;
-        const int smem = 1024 + kStemWBytes + 2 * buf + 2 * kStemN * 4 + 256;
+        const int set_bytes = (rows0 + rows1) * P;  // the residual planes follow the leading planes (same geometry)
+        const int buf = ((split ? 2 : 1) * set_bytes + kStemSlack + 127) / 128 * 128;
+        const int smem = 1024 + (split ? 2 : 1) * kStemWBytes + 2 * buf + 2 * kStemN * 4 + 256;
         if (smem > kStemMaxSmem) continue;
         p->H = H; p->W = W; p->Ho = Ho; p->Wo = Wo;
         p->T = T;
@@ -274,15 +318,16 @@ bool StemGeometry(int H, int W, SParams* p) {
         p->row_pitch = P;
         p->plane1_off = rows0 * P;
         p->buf_bytes = buf;
+        p->lo_off = split ? set_bytes : 0;
         p->tiles_per_strip = (T * p->spr + kTileM - 1) / kTileM;
         return true;
     }
     return false;
 }
 
-template <typename OutT>
+template <typename OutT, bool SPLIT = false>
 cudaError_t LaunchStem(const CUtensorMap& tm, const SParams& p, cudaStream_t stream) {
-    auto kern = stem_conv7x7_kernel<OutT>;
+    auto kern = stem_conv7x7_kernel<OutT, SPLIT>;
     static int sm_count[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -294,7 +339,7 @@ cudaError_t LaunchStem(const CUtensorMap& tm, const SParams& p, cudaStream_t str
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         sm_count[dev] = n > 0 ? n : 148;
     }
-    const int smem = 1024 + kStemWBytes + 2 * p.buf_bytes + 2 * kStemN * 4 + 256;
+    const int smem = 1024 + (SPLIT ? 2 : 1) * kStemWBytes + 2 * p.buf_bytes + 2 * kStemN * 4 + 256;
     const int grid = p.num_strips < sm_count[dev] ? p.num_strips : sm_count[dev];
     cudaError_t le = LaunchPdl(kern, grid, kThreads, smem, stream, tm, p);
     CountLaunch();
@@ -305,7 +350,7 @@ cudaError_t LaunchStem(const CUtensorMap& tm, const SParams& p, cudaStream_t str
 
 bool StemNchwSupported(const ConvArgs& a) {
     if (!a.stem_nchw) return false;
-    if ((!a.in_u8_hwc && a.in.dtype != DType::F32) || (a.out.dtype != DType::BF16 && a.out.dtype != DType::FP8)) return false;
+    if (!a.in_u8_hwc && a.in.dtype != DType::F32) return false;  // out F32 = FP32 mode (bf16-split operands)
     if (!StemFusable(a.Cin, a.Cout, a.R, a.S, a.stride, a.pad, a.in.H, a.in.W)) return false;
     if (a.pre_scale || a.pool2) return false;
     const int esz = (int)DTypeSize(a.out.dtype);
@@ -313,14 +358,14 @@ bool StemNchwSupported(const ConvArgs& a) {
     if (!a.in_u8_hwc && reinterpret_cast<uintptr_t>(a.in.base) % 16 != 0) return false;
     if (a.in_u8_hwc && reinterpret_cast<uintptr_t>(a.in_u8_hwc) % 4 != 0) return false;
     SParams p;
-    return StemGeometry(a.in.H, a.in.W, &p);
+    return StemGeometry(a.in.H, a.in.W, &p, a.out.dtype == DType::F32);
 }
 
 cudaError_t ConvStemNchw(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream) {
     if (!StemNchwSupported(a) || !w.tensor_map) return cudaErrorInvalidValue;
     if (a.n <= 0) return cudaSuccess;
     SParams p;
-    if (!StemGeometry(a.in.H, a.in.W, &p)) return cudaErrorInvalidValue;
+    if (!StemGeometry(a.in.H, a.in.W, &p, a.out.dtype == DType::F32)) return cudaErrorInvalidValue;
     if (p.Ho != a.out.H || p.Wo != a.out.W) return cudaErrorInvalidValue;
     p.in = reinterpret_cast<const float*>(a.in.base);
     p.in_u8 = a.in_u8_hwc;
@@ -332,6 +377,7 @@ cudaError_t ConvStemNchw(const ConvArgs& a, const UmmaWeights& w, cudaStream_t s
     p.out_pitch = a.out.pitch; p.out_coff = a.out.c_off; p.Cout = a.Cout;
     p.num_strips = a.n * p.strips_per_img;
     const CUtensorMap& tm = *reinterpret_cast<const CUtensorMap*>(w.tensor_map);
+    if (a.out.dtype == DType::F32) return LaunchStem<float, true>(tm, p, stream);
     if (a.out.dtype == DType::BF16) return LaunchStem<__nv_bfloat16>(tm, p, stream);
     return LaunchStem<__nv_fp8_e4m3>(tm, p, stream);
 }

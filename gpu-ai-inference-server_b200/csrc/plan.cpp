@@ -809,7 +809,11 @@ private:
     // The bf16 NHWC4 copy of an image input exists only to feed the stem conv; when that conv is the 7x7/s2 stem
     // the tcgen05 stem kernel converts fp32 NCHW rows on the fly, so the layout pass and its buffer disappear.
     void FuseStemInput() {
-        if (plan_.precision == Precision::FP32) return;
+        // FP32 mode runs the same kernel with bf16-split operands; only the exact-FFMA debug mode keeps the layout pass
+        if (plan_.precision == Precision::FP32) {
+            const char* e = getenv("B200_ENGINE_FP32_EXACT");
+            if (e && e[0] == '1') return;
+        }
         for (size_t k = 0; k < plan_.steps.size(); ++k) {
             if (plan_.steps[k].kind != StepKind::NchwToNhwc) continue;
             const int raw = plan_.steps[k].in, nhwc = plan_.steps[k].out;

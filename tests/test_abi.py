@@ -144,11 +144,11 @@ def test_planner_lowers_densenet_to_a_fused_static_plan(pkg, repo_dir, precision
     assert kinds.count("avgpool") == (3 if precision == "fp32" else 0)  # transitions pool in the conv prologue
     assert abs(d["flops_per_sample"] - 5.668e9) / 5.668e9 < 1e-3
     convs = [s for s in d["steps"] if s["kind"] == "conv"]
-    # tensor-core modes: the 7x7 stem reads the caller's fp32 NCHW batch directly (no layout pass, no bf16 copy)
-    assert kinds.count("nchw_to_nhwc") == (1 if precision == "fp32" else 0)
-    assert convs[0]["stem_nchw"] == (precision != "fp32") and convs[0]["R"] == 7
-    if precision != "fp32":
-        assert convs[0]["in"]["dtype"] == "f32" and convs[0]["in"]["C"] == 3
+    # every mode runs on tensor cores (fp32 with bf16-split operands): the 7x7 stem reads the caller's fp32 NCHW batch
+    # directly (no layout pass, no bf16 copy)
+    assert kinds.count("nchw_to_nhwc") == 0
+    assert convs[0]["stem_nchw"] and convs[0]["R"] == 7
+    assert convs[0]["in"]["dtype"] == "f32" and convs[0]["in"]["C"] == 3
     assert sum(1 for s in convs if s["pre_bn"]) == 58 + 3                  # dense layers + transitions
     assert sum(1 for s in convs if s["pool2_fused"]) == (0 if precision == "fp32" else 3)
     # dense layers write their 32 channels straight into the block buffer slice

@@ -58,7 +58,8 @@ barrier()
 m = reduce_max(10.0 + rank)          # MAX over ranks of the per-rank time
 assert m == 11.0, m
 barrier()
-print("RANK_OK", rank, flush=True)
+import os, sys
+os.write(1, ("RANK_OK %d\\n" % rank).encode())   # ONE write per rank: two ranks share the pipe and print() may interleave
 '''
 
 
