@@ -106,7 +106,7 @@ EXPORTED_SYMBOLS = [
 ]
 EXTENSION_SYMBOLS = [
     "B200EngineVersion", "B200PlanDescribe", "B200PlanShards", "B200KernelLaunchCount", "B200ModelStageInput", "B200ModelForwardDevice",
-    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats", "B200HostAlloc", "B200HostFree",
+    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats", "B200HostAlloc", "B200HostFree", "B200ModelInferTopK",
 ]
 
 
@@ -149,6 +149,7 @@ def load_library() -> C.CDLL:
         "B200ModelReadValue": (C.c_int64, [vp, cp, C.POINTER(C.c_float), sz, err]),
         "B200ModelCoalesceStats": (b, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "B200HostAlloc": (vp, [sz]), "B200HostFree": (None, [vp]),
+        "B200ModelInferTopK": (b, [vp, C.POINTER(CTensorData), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(vp)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here == missing export
@@ -380,6 +381,25 @@ class Model:
         return st
 
     # ---- extension API (include/b200_engine.h) ----
+    def infer_topk(self, inputs: Sequence[TensorData], k: int = 5, softmax: bool = True):
+        """Forward + softmax + top-k on the GPU (B200ModelInferTopK): returns (classes int32 [N,k], scores float32 [N,k])."""
+        if not self._h:
+            raise EngineError("model handle is nil")
+        keep: list = []
+        in_bufs = [np.ascontiguousarray(t.data, dtype=_NP_OF[DataType(t.data_type)]) for t in inputs]
+        cin = (CTensorData * len(inputs))(*[
+            _c_tensor(t.name.encode(), t.data_type, t.dims(), b, keep) for t, b in zip(inputs, in_bufs)])
+        n = int(inputs[0].dims()[0])
+        classes = np.zeros((n, k), np.int32)
+        scores = np.zeros((n, k), np.float32)
+        err = C.c_void_p()
+        ok = load_library().B200ModelInferTopK(self._h, cin, len(inputs), int(k), 1 if softmax else 0,
+                                               classes.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               scores.ctypes.data_as(C.POINTER(C.c_float)), C.byref(err))
+        if not ok:
+            raise EngineError(_take_error(err, "top-k inference failed"))
+        return classes, scores
+
     def coalesce_stats(self):
         """(batches executed by the request coalescer, requests they carried)"""
         nb, nr = C.c_int64(0), C.c_int64(0)

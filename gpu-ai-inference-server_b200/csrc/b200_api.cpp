@@ -163,6 +163,47 @@ int64_t B200ModelReadValue(ModelHandle handle, const char* value_name, float* ou
 }
 
 
+bool B200ModelInferTopK(ModelHandle handle, const TensorData* inputs, int num_inputs, int k, int apply_softmax, int32_t* classes,
+                        float* scores, ErrorMessage* error) {
+    std::shared_ptr<inference::Model> keep = B200ModelFromHandle(handle);
+    if (!keep) {
+        SetErr(error, "Invalid model handle");
+        return false;
+    }
+    if (!keep->IsLoaded()) {
+        SetErr(error, "Model not loaded");
+        return false;
+    }
+    if (!inputs || num_inputs <= 0 || k < 1 || k > b200::Replica::kMaxTopK || !classes || !scores) {
+        SetErr(error, "Invalid parameters");
+        return false;
+    }
+    try {
+        std::vector<inference::IoDesc> ins((size_t)num_inputs);
+        for (int i = 0; i < num_inputs; ++i) {
+            const TensorData& t = inputs[i];
+            ins[i].name = t.name ? t.name : "";
+            ins[i].dtype = (inference::DataType)(int)t.data_type;
+            if (t.shape.dims && t.shape.num_dims > 0) ins[i].dims.assign(t.shape.dims, t.shape.dims + t.shape.num_dims);
+            ins[i].data = t.data;
+            ins[i].bytes = t.data_size;
+        }
+        std::vector<inference::OutDesc> outs(1);
+        outs[0].topk = k;
+        outs[0].topk_softmax = apply_softmax != 0;
+        outs[0].topk_idx = classes;
+        outs[0].topk_val = scores;
+        if (!keep->Impl()->InferBorrowed(ins, outs)) {
+            SetErr(error, keep->GetLastError());
+            return false;
+        }
+        return true;
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return false;
+    }
+}
+
 bool B200ModelCoalesceStats(ModelHandle handle, int64_t* batches, int64_t* requests) {
     std::shared_ptr<inference::Model> keep;
     auto st = PinHandle(handle, &keep, nullptr);

@@ -148,6 +148,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
     };
 
     prepared_.resize(P.steps.size());
+    size_t f32_pool_need = 0;
     for (size_t i = 0; i < P.steps.size(); ++i) {
         const Step& s = P.steps[i];
         Prepared& pr = prepared_[i];
@@ -181,7 +182,23 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         // every convolution on the exact FFMA kernels
         const char* exact_env = getenv("B200_ENGINE_FP32_EXACT");
         const bool f32x3_enabled = !(exact_env && exact_env[0] == '1');
-        pr.use_f32x3 = !pr.use_umma && f32x3_enabled && kernels::ConvF32x3Supported(a);
+        kernels::ConvArgs a_eff = a;  // the conv the tensor cores actually run (a pooled transition multiplies the pooled operand)
+        if (!pr.use_umma && s.pool2_fused) {
+            // FP32 transition: sum_2x2 relu(bn(x)) is materialised once (kernels_poolbn.cu), then a plain 1x1 conv with out_mul 0.25
+            kernels::View vin = pr.in;
+            vin.C = s.Cin;
+            kernels::View pooled = vin;
+            pooled.base = arena_;
+            pooled.H = pr.out.H; pooled.W = pr.out.W; pooled.pitch = s.Cin; pooled.c_off = 0;
+            a_eff.in = pooled;
+            a_eff.pre_scale = a_eff.pre_shift = nullptr;
+            a_eff.pre_relu = false; a_eff.pool2 = false; a_eff.out_mul = 0.25f;
+            if (!f32x3_enabled || !a.pre_scale || !kernels::PoolBnRelu2x2Supported(vin, pooled) || !kernels::ConvF32x3Supported(a_eff))
+                throw CudaError("transition '" + s.name + "' was planned with its 2x2 average pool in front of the conv, which FP32 mode cannot run for this shape");
+            pr.split_pool = true;
+            f32_pool_need = std::max(f32_pool_need, (size_t)P.max_batch * pooled.H * pooled.W * s.Cin * 4 + 256);
+        }
+        pr.use_f32x3 = !pr.use_umma && f32x3_enabled && kernels::ConvF32x3Supported(a_eff);
         if (weights_of_) {  // same plan, same device: the lender's packed weights, scales and tensor map serve this instance too
             const Prepared& lp = weights_of_->prepared_[i];
             pr.w_kn = lp.w_kn;
@@ -190,7 +207,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         }
         if (pr.use_f32x3) {
             // [Cout_pad][R*S*Cin*2] bf16: per filter tap and 32 input channels one 128-byte row [w0 x32 | w1 x32], w = w0 + w1
-            const int bn = kernels::F32x3TileN(a);
+            const int bn = kernels::F32x3TileN(a_eff);
             const int cout_pad = (s.Cout + bn - 1) / bn * bn;
             const int K_pad = K * 2;
             std::vector<uint16_t> packed((size_t)cout_pad * K_pad, 0);
@@ -326,7 +343,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         // "1": only the wide ones (Cout > 128).  Default: transition 1 (one N tile) as well - the fused kernel's pooled transform
         // reads four planes through 8 warps and streams at 2.8 TB/s; the memory-bound pass + plain conv is 73 -> 60 us.
         const int min_cout = (e && e[0] == '1') ? 128 : 0;
-        size_t need = 0;
+        size_t need = f32_pool_need;
         for (size_t i = 0; enabled && i < P.steps.size(); ++i) {
             const Step& s = P.steps[i];
             Prepared& pr = prepared_[i];
@@ -545,7 +562,7 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
                 a.in = pooled;
                 a.pre_scale = a.pre_shift = nullptr;
                 a.pre_relu = false; a.pool2 = false; a.out_mul = 0.25f;
-                e = kernels::Conv1x1Tma(a, pr0.umma, stream_);
+                e = pr0.use_f32x3 ? kernels::ConvF32x3(a, pr0.umma, stream_) : kernels::Conv1x1Tma(a, pr0.umma, stream_);
                 break;
             }
             e = pr0.use_umma ? kernels::ConvUmma(a, pr0.umma, stream_)
@@ -625,7 +642,7 @@ void Replica::Enqueue(int n, int off, unsigned u8_mask) {
 }
 
 void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
-                  const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask, bool alone) {
+                  const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask, bool alone, const TopK* topk) {
     std::lock_guard<std::mutex> lk(mu_);
     DeviceGuard g(device_);
     const Plan& P = *plan_;
@@ -695,6 +712,21 @@ void Replica::Run(int n, const std::vector<const void*>& host_inputs, const std:
         size_t bytes = std::min((size_t)n * t.C * t.H * t.W * 4, out_capacity_bytes[i]);
         if (host_outputs[i] && bytes)
             CudaCheck(cudaMemcpyAsync(host_outputs[i], BufferPtr(t.buffer), bytes, cudaMemcpyDeviceToHost, stream_), "D2H output");
+    }
+    if (topk && topk->k > 0 && !P.outputs.empty()) {
+        if (topk->k > kMaxTopK || !topk->idx || !topk->val) throw CudaError("top-k: k must be 1.." + std::to_string(kMaxTopK) + " with both result arrays");
+        const TensorDesc& t = P.tensors[P.outputs[0]];
+        const size_t half = (size_t)P.max_batch * kMaxTopK * 4;
+        if (!topk_dev_) {
+            CudaCheck(cudaMalloc((void**)&topk_dev_, 2 * half), "cudaMalloc(top-k)");
+            allocations_.push_back(topk_dev_);
+            device_bytes_ += 2 * half;
+        }
+        int* d_idx = reinterpret_cast<int*>(topk_dev_);
+        float* d_val = reinterpret_cast<float*>(topk_dev_ + half);
+        CudaCheck(kernels::TopKRows((const float*)BufferPtr(t.buffer), n, t.C * t.H * t.W, topk->k, topk->softmax, d_idx, d_val, stream_), "top-k");
+        CudaCheck(cudaMemcpyAsync(topk->idx, d_idx, (size_t)n * topk->k * 4, cudaMemcpyDeviceToHost, stream_), "D2H top-k classes");
+        CudaCheck(cudaMemcpyAsync(topk->val, d_val, (size_t)n * topk->k * 4, cudaMemcpyDeviceToHost, stream_), "D2H top-k scores");
     }
     CudaCheck(cudaStreamSynchronize(stream_), "forward");
 }

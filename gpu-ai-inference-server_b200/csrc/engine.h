@@ -52,6 +52,7 @@ private:
 
 class Replica {
 public:
+    static constexpr int kMaxTopK = 64;
     // `weights_of`: another Replica of the SAME plan on the SAME device whose device-resident weights, constants, tensor maps and
     // dense-layer tables this one borrows (execution instances of one GPU share one read-only weight copy: one upload, one
     // quantisation pass, one L2 footprint).  The lender must outlive the borrower.
@@ -71,8 +72,16 @@ public:
     // graph's fp32 NCHW tensor - the uint8-ingestion extension of SURVEY.md section 8f.
     // `alone` = no other execution instance of this GPU is busy: only then is the batch cut into H2D/forward sub-batches
     // (with other requests in flight their forwards already hide this one's copy, and whole batches run more efficiently).
+    // `topk` (optional): softmax/top-k of graph output 0 is computed on the GPU after the forward and only k (class, score)
+    // pairs per sample travel back (host arrays of n * k entries).
+    struct TopK {
+        int k = 0;
+        bool softmax = false;
+        int32_t* idx = nullptr;
+        float* val = nullptr;
+    };
     void Run(int n, const std::vector<const void*>& host_inputs, const std::vector<void*>& host_outputs,
-             const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask = 0, bool alone = true);
+             const std::vector<size_t>& out_capacity_bytes, unsigned u8_mask = 0, bool alone = true, const TopK* topk = nullptr);
 
     // Several callers' requests as ONE batch (request coalescing): every segment's inputs are
     // copied from its own host buffers to consecutive sample offsets, one forward of the total runs, and every segment's
@@ -143,6 +152,7 @@ private:
     void* flush_buf_ = nullptr;
     void* splitk_scratch_ = nullptr;  // fp32 SIMT split-K: tile counters + partial sums (small batches)
     size_t splitk_bytes_ = 0;
+    char* topk_dev_ = nullptr;      // [max_batch][kMaxTopK] indices then values (allocated on first use)
     void* pool_scratch_ = nullptr;  // [max_batch][Ho][Wo][Cin] of the widest split transition
     size_t flush_bytes_ = 0;
     std::vector<void*> allocations_;

@@ -132,6 +132,8 @@ cudaError_t AddTensors(View a, View b, View out, int n, cudaStream_t stream);
 cudaError_t CopyChannels(View in, View out, int n, cudaStream_t stream);
 cudaError_t ReluTensor(View in, View out, int n, cudaStream_t stream);
 cudaError_t SoftmaxRows(const float* in, float* out, int rows, int cols, cudaStream_t stream);
+// top-k of every row (value descending, lowest index first among equals); `softmax`: values are softmax probabilities
+cudaError_t TopKRows(const float* in, int rows, int cols, int k, bool softmax, int* idx_out, float* val_out, cudaStream_t stream);
 cudaError_t FlushL2(void* scratch, size_t bytes, cudaStream_t stream);
 cudaError_t VectorAddF32(const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
 

@@ -71,10 +71,58 @@ __global__ void __launch_bounds__(kPbThreads) pool_bn_relu_2x2_kernel(const PbPa
     }
 }
 
+// FP32 mode: the same pass in fp32 (4 channels per 16-byte piece, (p0 + p1) + (p2 + p3) like the packed variants)
+__global__ void __launch_bounds__(kPbThreads) pool_bn_relu_2x2_f32_kernel(const PbParams p) {
+    __shared__ __align__(16) float s_sc[kPbMaxCin / 2], s_sh[kPbMaxCin / 2];
+    for (int i = threadIdx.x; i < p.Cin; i += kPbThreads) {
+        s_sc[i] = p.scale[i];
+        s_sh[i] = p.shift[i];
+    }
+    GridDepLaunch();
+    __syncthreads();
+    GridDepWait();
+    const size_t row_b = (size_t)p.W * p.in_pitch_b;
+    for (long long idx = (long long)blockIdx.x * kPbThreads + threadIdx.x; idx < p.total; idx += (long long)gridDim.x * kPbThreads) {
+        const int piece = (int)(idx % p.ppp);
+        const long long pix = idx / p.ppp;
+        const int ox = (int)(pix % p.Wo);
+        const long long t = pix / p.Wo;
+        const int oy = (int)(t % p.Ho);
+        const long long img = t / p.Ho;
+        const uint8_t* src = p.in + ((size_t)(img * p.H + 2 * oy) * p.W + 2 * ox) * p.in_pitch_b + p.in_coff_b + piece * 16;
+        uint4 q[4];
+        q[0] = LdgNc(src);
+        q[1] = LdgNc(src + p.in_pitch_b);
+        q[2] = LdgNc(src + row_b);
+        q[3] = LdgNc(src + row_b + p.in_pitch_b);
+        const float4 sc = *reinterpret_cast<const float4*>(&s_sc[piece * 4]);
+        const float4 sh = *reinterpret_cast<const float4*>(&s_sh[piece * 4]);
+        float y[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            y[k][0] = fmaf(__uint_as_float(q[k].x), sc.x, sh.x);
+            y[k][1] = fmaf(__uint_as_float(q[k].y), sc.y, sh.y);
+            y[k][2] = fmaf(__uint_as_float(q[k].z), sc.z, sh.z);
+            y[k][3] = fmaf(__uint_as_float(q[k].w), sc.w, sh.w);
+            if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) y[k][e] = fmaxf(y[k][e], 0.f);
+            }
+        }
+        float4 v;
+        v.x = (y[0][0] + y[1][0]) + (y[2][0] + y[3][0]);
+        v.y = (y[0][1] + y[1][1]) + (y[2][1] + y[3][1]);
+        v.z = (y[0][2] + y[1][2]) + (y[2][2] + y[3][2]);
+        v.w = (y[0][3] + y[1][3]) + (y[2][3] + y[3][3]);
+        *reinterpret_cast<float4*>(p.out + (size_t)pix * p.out_pitch_b + p.out_coff_b + piece * 16) = v;
+    }
+}
+
 }  // namespace
 
 bool PoolBnRelu2x2Supported(View in, View out) {
-    if (in.dtype != out.dtype || (in.dtype != DType::FP8 && in.dtype != DType::BF16)) return false;
+    if (in.dtype != out.dtype || (in.dtype != DType::FP8 && in.dtype != DType::BF16 && in.dtype != DType::F32)) return false;
+    if (in.dtype == DType::F32 && in.C > kPbMaxCin / 2) return false;
     const int esz = (int)DTypeSize(in.dtype);
     if (in.H != 2 * out.H || in.W != 2 * out.W || in.C != out.C || in.C > kPbMaxCin || (in.C * esz) % 16 != 0) return false;
     if ((in.pitch * esz) % 16 || (in.c_off * esz) % 16 || (out.pitch * esz) % 16 || (out.c_off * esz) % 16) return false;
@@ -100,8 +148,9 @@ cudaError_t PoolBnRelu2x2(View in, View out, int n, const float* scale, const fl
     long long blocks = (p.total + kPbThreads - 1) / kPbThreads;
     const long long cap = (long long)sms * 8;  // grid-stride: a multiple of the SM count
     if (blocks > cap) blocks = cap;
-    cudaError_t e = in.dtype == DType::FP8 ? LaunchPdl(pool_bn_relu_2x2_kernel<__nv_fp8_e4m3>, (int)blocks, kPbThreads, 0, stream, p)
-                                           : LaunchPdl(pool_bn_relu_2x2_kernel<__nv_bfloat16>, (int)blocks, kPbThreads, 0, stream, p);
+    cudaError_t e = in.dtype == DType::FP8    ? LaunchPdl(pool_bn_relu_2x2_kernel<__nv_fp8_e4m3>, (int)blocks, kPbThreads, 0, stream, p)
+                    : in.dtype == DType::BF16 ? LaunchPdl(pool_bn_relu_2x2_kernel<__nv_bfloat16>, (int)blocks, kPbThreads, 0, stream, p)
+                                              : LaunchPdl(pool_bn_relu_2x2_f32_kernel, (int)blocks, kPbThreads, 0, stream, p);
     CountLaunch();
     return e;
 }

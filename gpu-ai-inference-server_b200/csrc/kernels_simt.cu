@@ -1008,6 +1008,59 @@ cudaError_t SoftmaxRows(const float* in, float* out, int rows, int cols, cudaStr
     return cudaGetLastError();
 }
 
+// ---- on-device softmax + top-k: what the Go handler does per request with a full sort of the
+// 1000 logits (reference server/main.go:744-786).  One warp per row: softmax statistics (max, sum of exp), then k rounds of a
+// warp-wide argmax over the entries ranked below the previous pick (value descending, lowest index first among equals).
+__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ in, int rows, int cols, int k, int softmax,
+                                                        int* __restrict__ idx_out, float* __restrict__ val_out) {
+    const int row = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = in + (size_t)row * cols;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    if (softmax) {
+        for (int c = lane; c < cols; c += 32) sum += expf(x[c] - mx);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    float prev_v = INFINITY;
+    int prev_i = -1;
+    for (int r = 0; r < k; ++r) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < cols; c += 32) {
+            const float v = x[c];
+            const bool eligible = v < prev_v || (v == prev_v && c > prev_i);
+            if (eligible && (v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            const bool found = bi != 0x7fffffff;
+            idx_out[(size_t)row * k + r] = found ? bi : -1;
+            val_out[(size_t)row * k + r] = !found ? 0.f : softmax ? expf(bv - mx) / sum : bv;
+        }
+        prev_v = bv;
+        prev_i = bi;
+    }
+}
+
+cudaError_t TopKRows(const float* in, int rows, int cols, int k, bool softmax, int* idx_out, float* val_out, cudaStream_t stream) {
+    if (rows <= 0 || k <= 0) return cudaSuccess;
+    if (cols <= 0) return cudaErrorInvalidValue;
+    const int warps_per_block = 8;
+    topk_rows_kernel<<<(rows + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(in, rows, cols, k, softmax ? 1 : 0, idx_out, val_out);
+    CountLaunch();
+    return cudaGetLastError();
+}
+
 cudaError_t FlushL2(void* scratch, size_t bytes, cudaStream_t stream) {
     flush_kernel<<<148 * 8, 256, 0, stream>>>((uint4*)scratch, bytes / 16);
     return cudaGetLastError();

@@ -509,7 +509,8 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
                 }
                 ptrs[gi] = pin;
             }
-        if (coalesce_us_ > 0 && n <= coalesce_small_ && n < P.max_batch) ok = Coalesce(st, (int)n, ptrs, outs, u8_mask);
+        const bool wants_topk = !outs.empty() && outs[0].topk > 0;  // top-k requests carry their own result arrays: not coalesced
+        if (coalesce_us_ > 0 && n <= coalesce_small_ && n < P.max_batch && !wants_topk) ok = Coalesce(st, (int)n, ptrs, outs, u8_mask);
         else ok = Execute(*st, (int)n, ptrs, outs, u8_mask);
     } catch (const std::exception& e) {
         SetLastError(std::string("ONNX inference error: ") + e.what());
@@ -727,10 +728,17 @@ bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_pt
             op[i] = (char*)outs[i].data + begin;
             cap[i] = outs[i].capacity - begin;
         }
+        b200::Replica::TopK tk;
+        if (!outs.empty() && outs[0].topk > 0) {
+            tk.k = outs[0].topk;
+            tk.softmax = outs[0].topk_softmax;
+            tk.idx = outs[0].topk_idx + (size_t)s.off * tk.k;
+            tk.val = outs[0].topk_val + (size_t)s.off * tk.k;
+        }
         int slot = 0;
         bool alone = true;
         b200::Replica* r = st.Acquire(s.replica, &slot, &alone);
-        try { r->Run(s.cnt, ip, op, cap, u8_mask, alone); } catch (...) { st.Release(slot); throw; }
+        try { r->Run(s.cnt, ip, op, cap, u8_mask, alone, tk.k > 0 ? &tk : nullptr); } catch (...) { st.Release(slot); throw; }
         st.Release(slot);
     };
     if (single) {

@@ -28,6 +28,11 @@ struct OutDesc {
     void* data = nullptr;       // caller buffer (may be null: nothing is copied)
     size_t capacity = 0;        // bytes available at `data`
     size_t produced = 0;        // bytes the engine produced for this output
+    // extension (B200ModelInferTopK, output 0 only): softmax/top-k on the GPU, k (class, score) pairs per sample
+    int topk = 0;
+    bool topk_softmax = false;
+    int32_t* topk_idx = nullptr;
+    float* topk_val = nullptr;
 };
 
 // One contiguous piece of a batch assigned to one GPU replica.

@@ -634,7 +634,14 @@ private:
             produced = g_.nodes[c1].outputs[0];
             c1 = SoleConsumer(Canon(produced));
         }
-        if (plan_.precision != Precision::FP32 && !st.post_relu && R == 1 && S == 1 && stride == 1 && pad == 0 &&
+        // FP32 mode commutes the pool as well when the pooled-operand pass + split-operand 1x1 kernel take the shape
+        // (kernels_poolbn.cu, kernels_f32x3.cu); the exact-FFMA debug mode keeps conv -> AveragePool
+        bool pool_ok = plan_.precision != Precision::FP32;
+        if (!pool_ok) {
+            const char* e = getenv("B200_ENGINE_FP32_EXACT");
+            pool_ok = !(e && e[0] == '1') && st.pre_scale >= 0 && st.Cin % 32 == 0 && st.Cout % 32 == 0 && st.Cin <= 1024 && st.Cout <= 1024;
+        }
+        if (pool_ok && !st.post_relu && R == 1 && S == 1 && stride == 1 && pad == 0 &&
             c1 >= 0 && g_.nodes[c1].op_type == "AveragePool" && !skipped_.count(c1)) {
             const auto& pn = g_.nodes[c1];
             auto k = pn.GetInts("kernel_shape");

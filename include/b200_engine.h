@@ -68,6 +68,14 @@ char* B200ModelProfileSteps(ModelHandle handle, int batch, int repeats, ErrorMes
 int64_t B200ModelReadValue(ModelHandle handle, const char* value_name, float* out, size_t out_elems,
                            ErrorMessage* error);
 
+/* ModelInfer with the classification tail on the GPU: runs the forward exactly like ModelInfer
+ * (same input rules, FLOAT32 NCHW or UINT8 NHWC pixels), then softmax (if apply_softmax != 0) and top-k of graph output 0 on the
+ * device; only k (class index, score) pairs per sample come back.  `classes` / `scores` are caller arrays of N * k entries, row
+ * major, best first (equal scores: lowest class index first).  Replaces the full sort of 1000 floats per request in the Go
+ * handler (reference server/main.go:744-786).  1 <= k <= 64. */
+bool B200ModelInferTopK(ModelHandle handle, const TensorData* inputs, int num_inputs, int k, int apply_softmax, int32_t* classes,
+                        float* scores, ErrorMessage* error);
+
 /* Page-locked host memory for request buffers (copy elimination at the boundary): a caller
  * that fills buffers from B200HostAlloc (cgo: C.B200HostAlloc instead of C.malloc, inference_binding.go:670-700) lets
  * ModelInfer DMA straight from / into them; pageable buffers work too but go through the driver's staging copy.

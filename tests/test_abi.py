@@ -141,7 +141,7 @@ def test_planner_lowers_densenet_to_a_fused_static_plan(pkg, repo_dir, precision
     assert kinds.count("bn_relu") == 0 and kinds.count("relu") == 0   # all 62 BN / 121 ReLU folded away
     assert kinds.count("copy_channels") == 0 and d["inplace_concats"] == 58 and d["copied_concats"] == 0
     assert kinds.count("global_avgpool") == 1 and kinds.count("maxpool") == 1
-    assert kinds.count("avgpool") == (3 if precision == "fp32" else 0)  # transitions pool in the conv prologue
+    assert kinds.count("avgpool") == 0                                  # transitions pool in front of the conv
     assert abs(d["flops_per_sample"] - 5.668e9) / 5.668e9 < 1e-3
     convs = [s for s in d["steps"] if s["kind"] == "conv"]
     # every mode runs on tensor cores (fp32 with bf16-split operands): the 7x7 stem reads the caller's fp32 NCHW batch
@@ -150,7 +150,7 @@ def test_planner_lowers_densenet_to_a_fused_static_plan(pkg, repo_dir, precision
     assert convs[0]["stem_nchw"] and convs[0]["R"] == 7
     assert convs[0]["in"]["dtype"] == "f32" and convs[0]["in"]["C"] == 3
     assert sum(1 for s in convs if s["pre_bn"]) == 58 + 3                  # dense layers + transitions
-    assert sum(1 for s in convs if s["pool2_fused"]) == (0 if precision == "fp32" else 3)
+    assert sum(1 for s in convs if s["pool2_fused"]) == 3
     # dense layers write their 32 channels straight into the block buffer slice
     c33 = [s for s in convs if s["R"] == 3]
     assert len(c33) == 58 and all(s["out"]["pitch"] > s["out"]["C"] == 32 for s in c33)

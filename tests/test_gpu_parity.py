@@ -533,3 +533,91 @@ def test_multi_gpu_batch_sharding_matches_single_gpu(pkg, repo_dir, monkeypatch)
         finally:
             mgr.shutdown()
     assert np.array_equal(outs["0"], outs["all"])     # same kernels, same per-image arithmetic: bit-identical
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The C++ API, exercised by native programs
+def _run_native(cmd, monkeypatch, timeout=300):
+    import subprocess
+    env = dict(os.environ, B200_ENGINE_DEVICES="0", B200_ENGINE_PRECISION="fp32", B200_ENGINE_MAX_BATCH="4")
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+
+
+def test_reference_onnx_test_program_runs_unmodified(repo_dir, monkeypatch):
+    """`/root/reference/test/onnx_test.cpp` compiled UNMODIFIED against include/ + the .so (oracle/build_ref_tests.py): it loads
+    models/test_model through `inference::Model`, feeds [[1, 1, 1]] (onnx_test.cpp:92) and prints the output tensor."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "onnx_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/onnx_test was not built (the reference mount was absent at build time)")
+    r = _run_native([exe, os.path.join(repo_dir, "test_model", "1")], monkeypatch)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "Model loaded successfully!" in r.stdout and "Inference completed successfully!" in r.stdout
+    assert "Inputs: input" in r.stdout and "Outputs: output" in r.stdout and "Shape: [1, 2]" in r.stdout
+    vals = [ln for ln in r.stdout.splitlines() if ln.startswith("First 2 values:")]
+    got = np.array([float(t) for t in vals[0].split(":")[1].split()], np.float32)
+    with open(os.path.join(ROOT, "tests", "golden", "test_model_kat.json")) as fh:
+        kat = [v for v in json.load(fh)["vectors"] if v["input"] == [[1.0, 1.0, 1.0]]][0]
+    np.testing.assert_allclose(got, np.asarray(kat["output"], np.float32).ravel(), rtol=2e-5)   # printed with 6 digits
+    assert "Inference Count: 1" in r.stdout and "Model unloaded successfully!" in r.stdout
+
+
+def test_reference_cuda_test_program_runs_unmodified(monkeypatch):
+    exe = os.path.join(ROOT, "oracle", "_ref", "cuda_test")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/cuda_test was not built (the reference mount was absent at build time)")
+    r = _run_native([exe], monkeypatch)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "CUDA Available: Yes" in r.stdout and "Compute Capability 10." in r.stdout
+    assert "Vector addition succeeded" in r.stdout and r.stdout.count("1 + 1 = 2 ✓") == 5
+
+
+def test_cpp_inference_manager_run_inference_and_tensor(repo_dir, densenet_path, tmp_path, monkeypatch):
+    """tests/cpp/api_test.cpp: `inference::Tensor` (SetData/GetData/Reshape/copy/toGPU/toCPU, reference model.cpp:30-436) and
+    `inference::InferenceManager` (LoadModel / LoadModelAsync / RunInference / UnloadModelAsync, reference
+    inference_manager.cpp:283-384,674-707) at run time, results against the golden vector and the oracle."""
+    exe = os.path.join(ROOT, "build", "api_test")
+    assert os.path.exists(exe), "build/api_test missing: run __graft_entry__.build()"
+    n = 2
+    x = synth.to_model_input(synth.synthetic_images_u8(n, start=7000))
+    f = tmp_path / "x.f32"
+    x.astype(np.float32).tofile(str(f))
+    r = _run_native([exe, repo_dir, str(f), str(n)], monkeypatch)
+    fails = [ln for ln in r.stdout.splitlines() if ln.startswith("FAIL")]
+    assert r.returncode == 0 and not fails, (fails, r.stdout[-1500:], r.stderr[-1500:])
+    assert r.stdout.count("ok tensor.") >= 13 and "ok mgr.run_inference" in r.stdout and "ok dense.run_inference" in r.stdout
+    kat = [ln.split()[1:] for ln in r.stdout.splitlines() if ln.startswith("KAT ")][0]
+    np.testing.assert_allclose(np.array(kat, np.float64), [-1.6748662, 2.0709436], rtol=2e-6)
+    ref = OnnxOracle(densenet_path).run({"data_0": x})[0]
+    dense = [ln.split()[1:] for ln in r.stdout.splitlines() if ln.startswith("DENSE ")]
+    assert len(dense) == n
+    for i, arg, mx in dense:
+        assert int(arg) == int(ref[int(i)].argmax())
+        assert abs(float(mx) - float(ref[int(i)].max())) / np.abs(ref).max() < 1e-3
+
+
+def test_on_device_softmax_top5_matches_a_host_sort(pkg, repo_dir, monkeypatch):
+    """B200ModelInferTopK = ModelInfer + softmax + top-k on the GPU; the reference's Go handler sorts
+    all 1000 probabilities per request (server/main.go:744-786).  Same classes and scores as sorting the logits of ModelInfer."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "fp32")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "4")          # 7 images through a 4-image arena: two shards
+    u8 = synth.synthetic_images_u8(7, start=8000)
+    x = synth.to_model_input(u8)
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        logits = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [7, 1000])])[0].data.astype(np.float64)
+        prob = np.exp(logits - logits.max(1, keepdims=True))
+        prob /= prob.sum(1, keepdims=True)
+        order = np.argsort(-logits, axis=1, kind="stable")[:, :5]
+        for inp in (pkg.TensorData("data_0", x), pkg.TensorData("data_0", np.ascontiguousarray(u8), pkg.DataType.UINT8)):
+            classes, scores = m.infer_topk([inp], k=5, softmax=True)
+            assert classes.shape == (7, 5) and np.array_equal(classes, order)
+            np.testing.assert_allclose(scores, np.take_along_axis(prob, order, 1), rtol=2e-5, atol=1e-9)
+        classes, raw = m.infer_topk([pkg.TensorData("data_0", x)], k=3, softmax=False)
+        assert np.array_equal(classes, order[:, :3])
+        np.testing.assert_allclose(raw, np.take_along_axis(logits, order[:, :3], 1), rtol=1e-6)
+        with pytest.raises(pkg.EngineError, match="Invalid parameters"):
+            m.infer_topk([pkg.TensorData("data_0", x)], k=65)
+    finally:
+        mgr.shutdown()
