@@ -106,7 +106,7 @@ EXPORTED_SYMBOLS = [
 ]
 EXTENSION_SYMBOLS = [
     "B200EngineVersion", "B200PlanDescribe", "B200PlanShards", "B200KernelLaunchCount", "B200ModelStageInput", "B200ModelForwardDevice",
-    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats", "B200HostAlloc", "B200HostFree", "B200ModelInferTopK",
+    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats", "B200HostAlloc", "B200HostFree", "B200ModelInferTopK", "B200ModelFaultedReplicas",
 ]
 
 
@@ -149,6 +149,7 @@ def load_library() -> C.CDLL:
         "B200ModelReadValue": (C.c_int64, [vp, cp, C.POINTER(C.c_float), sz, err]),
         "B200ModelCoalesceStats": (b, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "B200HostAlloc": (vp, [sz]), "B200HostFree": (None, [vp]),
+        "B200ModelFaultedReplicas": (i, [vp]),
         "B200ModelInferTopK": (b, [vp, C.POINTER(CTensorData), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(vp)]),
     }
     for name, (res, args) in sig.items():
@@ -399,6 +400,10 @@ class Model:
         if not ok:
             raise EngineError(_take_error(err, "top-k inference failed"))
         return classes, scores
+
+    def faulted_replicas(self) -> int:
+        """GPU replicas dropped from the shard set after a CUDA error."""
+        return int(load_library().B200ModelFaultedReplicas(self._h))
 
     def coalesce_stats(self):
         """(batches executed by the request coalescer, requests they carried)"""

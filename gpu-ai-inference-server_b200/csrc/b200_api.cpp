@@ -204,6 +204,11 @@ bool B200ModelInferTopK(ModelHandle handle, const TensorData* inputs, int num_in
     }
 }
 
+int B200ModelFaultedReplicas(ModelHandle handle) {
+    std::shared_ptr<inference::Model> keep = B200ModelFromHandle(handle);
+    return keep ? keep->Impl()->FaultedReplicas() : 0;
+}
+
 bool B200ModelCoalesceStats(ModelHandle handle, int64_t* batches, int64_t* requests) {
     std::shared_ptr<inference::Model> keep;
     auto st = PinHandle(handle, &keep, nullptr);

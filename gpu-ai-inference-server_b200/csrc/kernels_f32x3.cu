@@ -336,28 +336,30 @@ cudaError_t LaunchFsL1(const CUtensorMap& tw, const CUtensorMap& tin, const CUte
 }
 
 // =====================================================================================================================
-// 3x3 / stride 1 / pad 1 convolution of Cin (multiple of 32) fp32 channels into <= 32 channels
+// 3x3 / stride 1 / pad 1 convolution of Cin <= 128 (multiple of 32) fp32 channels into <= 32 channels
 // =====================================================================================================================
 // Same geometry as kernels_conv3x3.cu (one 4-D TMA box lands the zero-padded patch, nine row-shifted descriptors are the nine
 // taps), but a pixel is Cin*4 bytes, so the K dimension is walked in 32-channel PLANES: a pipeline stage = one plane of the
-// patch ((TH+2) x 16 slots x 128 B, split in place by the transform warps) + that plane's nine weight tiles
-// ([32][128 B] each, streamed from L2 - all planes of the weights do not fit next to the patch ring).
+// patch ((TH+2) x 16 slots x 128 B), split in place by the transform warps.  All weights stay resident (144 KB for Cin = 128).
+//
+// N = 32 output channels makes every MMA A-fetch bound (4 KB of A per 16 cycles of math), so the three products per term are
+// issued as TWO A fetches instead of three: the weight tile stacks [w0 ; w1] along N (64 rows: rows 0-31 the leading terms,
+// rows 32-63 the residuals of the same 32 output channels) and
+//     a0 x [w0 ; w1]  (N = 64)  ->  columns 0-31 += a0*w0, columns 32-63 += a0*w1
+//     a1 x  w0        (N = 32)  ->  columns 0-31 += a1*w0
+// the epilogue adds the two column halves.  A weight tile row is 128 B = two planes of one tap ([plane 2p | plane 2p+1]),
+// so the resident set is [tap][plane pair][64 rows][128 B].
 constexpr int kF3Threads = 32 * 14;   // 8 transform + 4 epilogue + TMA + MMA
 constexpr int kF3XfWarps = 8;
 constexpr int kF3PW = 16;
 constexpr int kF3PatchBytes = 10 * kF3PW * 128;
-constexpr int kF3WBytes = 9 * 32 * 128;                    // the nine weight tiles of ONE 32-channel plane
+constexpr int kF3WTile = 64 * 128;                         // one (tap, plane pair) weight tile
 constexpr int kF3Acc = 4;
-constexpr int kF3ResPlanes = 4;                            // resident-weight variant: Cin <= 128
-// RESW: all planes of the weights stay resident (144 KB for Cin = 128) and a stage is one 20 KB patch plane; otherwise every
-// stage also carries its plane's weights, streamed from L2 (227 KB instead of 80 KB of L2->SM traffic per tile of a 128-channel
-// layer: measured 320 us per 56x56 layer at bs256).
-template <bool RESW> struct F3Cfg {
-    static constexpr int kStageBytes = kF3PatchBytes + (RESW ? 0 : kF3WBytes);
-    static constexpr int kStages = RESW ? 4 : 3;
-    static constexpr int kResBytes = RESW ? kF3ResPlanes * kF3WBytes : 0;
-    static constexpr int kSmemBytes = 1024 + kResBytes + kStages * kStageBytes + 1024 /*junk-row overreach*/ + 256;
-};
+constexpr int kF3AccCols = 64;
+constexpr int kF3MaxPlanes = 4;                            // Cin <= 128
+constexpr int kF3Stages = 4;
+constexpr int kF3ResBytes = 9 * (kF3MaxPlanes / 2) * kF3WTile;
+constexpr int kF3SmemBytes = 1024 + kF3ResBytes + kF3Stages * kF3PatchBytes + 1024 /*junk-row overreach*/ + 512;
 
 struct FsC3Params {
     float* out;
@@ -369,26 +371,27 @@ struct FsC3Params {
     int planes;  // Cin / 32
 };
 
-template <bool RESW>
 __global__ void __launch_bounds__(kF3Threads, 1)
 conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_in, const FsC3Params p) {
-    using Cfg = F3Cfg<RESW>;
-    constexpr int NS = Cfg::kStages;
-    constexpr int kF3StageBytes = Cfg::kStageBytes;
+    constexpr int NS = kF3Stages;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* s_w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // RESW: [plane][tap][32][128 B]
-    uint8_t* smem = s_w + Cfg::kResBytes;
-    uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem + NS * kF3StageBytes + 1024);
+    uint8_t* s_w = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = s_w + kF3ResBytes;
+    uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem + NS * kF3PatchBytes + 1024);
     uint64_t* xf_full = raw_full + NS;
     uint64_t* empty_bar = xf_full + NS;
     uint64_t* tmem_full = empty_bar + NS;
     uint64_t* tmem_empty = tmem_full + kF3Acc;
     uint64_t* w_bar = tmem_empty + kF3Acc;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    float* s_sc = reinterpret_cast<float*>(tmem_slot + 4);  // 16-byte aligned: (3*4 + 2*4 + 1) * 8 + 16 = 184 -> 192
+    s_sc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_sc) + 15) & ~(uintptr_t)15);
+    float* s_bi = s_sc + 32;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kNW = kF3Threads / 32;
     const int wrole = warp >= kNW - 2 ? warp - (kNW - 2) : warp + 2;  // 0 TMA, 1 MMA, 2..9 transform, 10..13 epilogue
+    const int npairs = (p.planes + 1) >> 1;
 
     if (wrole == 0 && lane == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -405,7 +408,11 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         PrefetchTensorMap(&tmap_w);
         PrefetchTensorMap(&tmap_in);
     }
-    if (wrole == 1) TmemAlloc(tmem_slot, kF3Acc * 32);
+    if (wrole == 1) TmemAlloc(tmem_slot, kF3Acc * kF3AccCols);
+    if (threadIdx.x < 32) {
+        s_sc[threadIdx.x] = (int)threadIdx.x < p.Cout ? p.out_scale[threadIdx.x] : 0.f;
+        s_bi[threadIdx.x] = (p.bias && (int)threadIdx.x < p.Cout) ? p.bias[threadIdx.x] : 0.f;
+    }
     TcFenceBefore();
     __syncthreads();
     TcFenceAfter();
@@ -413,17 +420,14 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     GridDepLaunch();
 
     if (wrole == 0) {
-        // =========================================================== TMA producer: (tile, plane) stages
-        if (RESW) {  // the weights do not depend on the previous kernel: load them before the dependency wait
-            if (ElectOne()) {
-                MbarArriveExpectTx(w_bar, (uint32_t)(p.planes * kF3WBytes));
-                for (int j = 0; j < p.planes; ++j)
-                    for (int t = 0; t < 9; ++t) TmaLoad2D(s_w + (j * 9 + t) * 4096, &tmap_w, w_bar, (t * p.planes + j) * 64, 0);
-            }
-            __syncwarp();
+        // =========================================================== TMA producer: resident weights, then (tile, plane) stages
+        if (ElectOne()) {  // the weights do not depend on the previous kernel: load them before the dependency wait
+            MbarArriveExpectTx(w_bar, (uint32_t)(9 * npairs * kF3WTile));
+            for (int t = 0; t < 9 * npairs; ++t) TmaLoad2D(s_w + t * kF3WTile, &tmap_w, w_bar, t * 64, 0);
         }
+        __syncwarp();
         GridDepWait();
-        const uint32_t stage_tx = (uint32_t)((p.TH + 2) * kF3PW * 128 + (RESW ? 0 : kF3WBytes));
+        const uint32_t stage_tx = (uint32_t)((p.TH + 2) * kF3PW * 128);
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -431,14 +435,8 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             for (int j = 0; j < p.planes; ++j) {
                 MbarWaitWarp(&empty_bar[stage], phase ^ 1u);
                 if (ElectOne()) {
-                    uint8_t* dst = smem + stage * kF3StageBytes;
                     MbarArriveExpectTx(&raw_full[stage], stage_tx);
-                    TmaLoad4D(dst, &tmap_in, &raw_full[stage], p.in_coff + j * kFsCH, tx * p.TW - 1, ty * p.TH - 1, img);
-                    if (!RESW) {
-#pragma unroll
-                        for (int t = 0; t < 9; ++t)
-                            TmaLoad2D(dst + kF3PatchBytes + t * 4096, &tmap_w, &raw_full[stage], (t * p.planes + j) * 64, 0);
-                    }
+                    TmaLoad4D(smem + stage * kF3PatchBytes, &tmap_in, &raw_full[stage], p.in_coff + j * kFsCH, tx * p.TW - 1, ty * p.TH - 1, img);
                 }
                 __syncwarp();
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -446,27 +444,31 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         }
     } else if (wrole == 1) {
         // =========================================================== MMA issuer
-        constexpr uint32_t idesc = MakeInstrDesc(1 /*BF16*/, 32);
-        const uint32_t smem_u = SmemAddr(smem);
+        constexpr uint32_t idesc64 = MakeInstrDesc(1 /*BF16*/, 64), idesc32 = MakeInstrDesc(1, 32);
+        const uint32_t smem_u = SmemAddr(smem), w_u = SmemAddr(s_w);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        if (RESW) MbarWaitWarp(w_bar, 0);
+        MbarWaitWarp(w_bar, 0);
         int stage = 0;
         uint32_t phase = 0, k = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++k) {
             const uint32_t acc = k % kF3Acc, acc_ph = (k / kF3Acc) & 1u;
             MbarWaitWarp(&tmem_empty[acc], acc_ph ^ 1u);
             TcFenceAfter();
-            const uint32_t d_addr = tmem_u + acc * 32;
+            const uint32_t d_addr = tmem_u + acc * kF3AccCols;
             for (int j = 0; j < p.planes; ++j) {
                 MbarWaitWarp(&xf_full[stage], phase);
                 TcFenceAfter();
                 if (ElectOne()) {
-                    const uint32_t a_buf = smem_u + stage * kF3StageBytes;
-                    const uint64_t b_base = MakeSmemDesc(RESW ? SmemAddr(s_w) + j * kF3WBytes : a_buf + kF3PatchBytes);
+                    const uint32_t a_buf = smem_u + stage * kF3PatchBytes;
+                    const uint32_t b_plane = w_u + (j >> 1) * kF3WTile + (j & 1) * 64;  // this plane's 64-byte half of the pair tile
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const uint64_t a_desc = MakeSmemDesc(a_buf + ((tap / 3) * kF3PW + (tap % 3)) * 128);
-                        IssueSplitChunk(d_addr, a_desc, b_base + (uint64_t)(tap * (4096 >> 4)), idesc, j == 0 && tap == 0);
+                        const uint64_t b_desc = MakeSmemDesc(b_plane + tap * npairs * kF3WTile);
+                        UmmaSS<0>(d_addr, a_desc + 0, b_desc + 0, idesc64, (j | tap) ? 1u : 0u);  // a0 x [w0 ; w1]
+                        UmmaSS<0>(d_addr, a_desc + 2, b_desc + 2, idesc64, 1u);
+                        UmmaSS<0>(d_addr, a_desc + 4, b_desc + 0, idesc32, 1u);                   // a1 x w0
+                        UmmaSS<0>(d_addr, a_desc + 6, b_desc + 2, idesc32, 1u);
                     }
                     UmmaCommit(&empty_bar[stage]);
                     if (j == p.planes - 1) UmmaCommit(&tmem_full[acc]);
@@ -488,7 +490,7 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 MbarWaitWarp(&raw_full[stage], phase);
                 for (int u = tw; u < units; u += kF3XfWarps) {
                     const int row = u * 16 + (lane & 15);
-                    SplitHalfRow<false>(smem_u + stage * kF3StageBytes + row * 128, row, half, 0, 0, false);
+                    SplitHalfRow<false>(smem_u + stage * kF3PatchBytes + row * 128, row, half, 0, 0, false);
                 }
                 FenceProxyAsync();
                 __syncwarp();
@@ -499,12 +501,7 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     } else {
         // =========================================================== epilogue
         const int e = warp & 3;  // TMEM lane quarter
-        float sc[32], bi[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            sc[q] = q < p.Cout ? p.out_scale[q] : 0.f;
-            bi[q] = (p.bias && q < p.Cout) ? p.bias[q] : 0.f;
-        }
+        const uint32_t sc_addr = SmemAddr(s_sc), bi_addr = SmemAddr(s_bi);
         const int mrow = e * 32 + lane;
         const int y = mrow / kF3PW, x = mrow - y * kF3PW;
         GridDepWait();  // stores may alias buffers the previous kernel still reads
@@ -514,8 +511,9 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
             MbarWaitWarp(&tmem_full[acc], acc_phase);
             TcFenceAfter();
-            uint32_t r[32];
-            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * 32, r);
+            uint32_t r[32], r1[32];
+            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kF3AccCols, r);
+            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kF3AccCols + 32, r1);
             TmemLoadWait();
             TcFenceBefore();
             __syncwarp();
@@ -526,11 +524,12 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     if (q * 4 < p.Cout) {
+                        const float4 s4 = LdsF4(sc_addr + q * 16), b4 = LdsF4(bi_addr + q * 16);
                         float4 v;
-                        v.x = fmaf(__uint_as_float(r[4 * q]), sc[4 * q], bi[4 * q]);
-                        v.y = fmaf(__uint_as_float(r[4 * q + 1]), sc[4 * q + 1], bi[4 * q + 1]);
-                        v.z = fmaf(__uint_as_float(r[4 * q + 2]), sc[4 * q + 2], bi[4 * q + 2]);
-                        v.w = fmaf(__uint_as_float(r[4 * q + 3]), sc[4 * q + 3], bi[4 * q + 3]);
+                        v.x = fmaf(__uint_as_float(r[4 * q]) + __uint_as_float(r1[4 * q]), s4.x, b4.x);
+                        v.y = fmaf(__uint_as_float(r[4 * q + 1]) + __uint_as_float(r1[4 * q + 1]), s4.y, b4.y);
+                        v.z = fmaf(__uint_as_float(r[4 * q + 2]) + __uint_as_float(r1[4 * q + 2]), s4.z, b4.z);
+                        v.w = fmaf(__uint_as_float(r[4 * q + 3]) + __uint_as_float(r1[4 * q + 3]), s4.w, b4.w);
                         if (p.post_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                         *reinterpret_cast<float4*>(orow + q * 4) = v;
                     }
@@ -543,7 +542,7 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     __syncthreads();
     if (wrole == 1) {
         TcFenceAfter();
-        TmemDealloc(tmem_base, kF3Acc * 32);
+        TmemDealloc(tmem_base, kF3Acc * kF3AccCols);
     }
 }
 
@@ -559,17 +558,30 @@ bool ConvF32x3Supported(const ConvArgs& a) {
     if (reinterpret_cast<uintptr_t>(a.in.base) % 16 != 0 || reinterpret_cast<uintptr_t>(a.out.base) % 16 != 0) return false;
     if (a.in.c_off + a.Cin > a.in.pitch) return false;
     if (Is1x1(a)) return a.Cin <= kFsMaxC && a.Cout % 32 == 0 && a.Cout >= 32 && a.Cout <= kFsMaxC;
-    if (Is3x3(a)) return !a.pre_scale && a.Cout <= 32 && a.Cout % 4 == 0 && a.Cout >= 4 && a.in.H >= 1 && a.in.W >= 1;
+    if (Is3x3(a)) return !a.pre_scale && a.Cin <= 32 * kF3MaxPlanes && a.Cout <= 32 && a.Cout % 4 == 0 && a.Cout >= 4 && a.in.H >= 1 && a.in.W >= 1;
     return false;
 }
 
 int F32x3TileN(const ConvArgs& a) {
-    if (Is3x3(a)) return 32;
+    if (Is3x3(a)) return 64;  // [w0 ; w1] stacked along N
     return a.Cout % 128 == 0 ? 128 : a.Cout % 64 == 0 ? 64 : 32;
 }
+bool F32x3StackedN(const ConvArgs& a) { return Is3x3(a); }
+int F32x3PackedK(const ConvArgs& a) {
+    if (Is3x3(a)) return 9 * ((a.Cin / 32 + 1) / 2) * 64;
+    return a.R * a.S * a.Cin * 2;
+}
 
-// bf16 element index of input channel c of filter tap `tap` inside a packed weight row; the residual term sits 32 further
-int F32x3WeightIndex(int tap, int c, int Cin) { return (tap * (Cin / 32) + c / 32) * 64 + (c % 32); }
+// bf16 element index of input channel c of filter tap `tap` inside a packed weight row.  1x1: the residual term sits 32
+// elements further in the same row.  3x3 (stacked N): the residual term sits in row Cout + 32 at the same index; one 128-byte
+// row piece holds two 32-channel planes of one tap.
+int F32x3WeightIndex(const ConvArgs& a, int tap, int c) {
+    if (Is3x3(a)) {
+        const int plane = c / 32, npairs = (a.Cin / 32 + 1) / 2;
+        return (tap * npairs + plane / 2) * 64 + (plane & 1) * 32 + (c % 32);
+    }
+    return (tap * (a.Cin / 32) + c / 32) * 64 + (c % 32);
+}
 
 cudaError_t ConvF32x3(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream) {
     if (!ConvF32x3Supported(a) || !w.tensor_map) return cudaErrorInvalidValue;
@@ -629,14 +641,11 @@ cudaError_t ConvF32x3(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stre
     cudaGetDevice(&dev);
     dev &= 63;
     if (!attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_f32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3Cfg<true>::kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_f32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3Cfg<false>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_f32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF3SmemBytes);
         if (e != cudaSuccess) return e;
         attr_set[dev] = true;
     }
-    cudaError_t le = p.planes <= kF3ResPlanes
-        ? LaunchPdl(conv3x3_f32x3_kernel<true>, grid, kF3Threads, F3Cfg<true>::kSmemBytes, stream, tw, ti, p)
-        : LaunchPdl(conv3x3_f32x3_kernel<false>, grid, kF3Threads, F3Cfg<false>::kSmemBytes, stream, tw, ti, p);
+    cudaError_t le = LaunchPdl(conv3x3_f32x3_kernel, grid, kF3Threads, kF3SmemBytes, stream, tw, ti, p);
     CountLaunch();
     return le;
 }

@@ -296,6 +296,10 @@ bool ModelImpl::Load() {
                 st->extra.emplace_back(new b200::Replica(d, plan, graphs, chains[di], st->replicas[di].get()));
                 mem += st->extra.back()->DeviceBytes();
             }
+        st->faulted = std::vector<std::atomic<int>>(st->replicas.size());
+        for (auto& f : st->faulted) f.store(0);
+        if (st->replicas.size() > 1) st->workers.reset(new GpuWorkers((int)st->replicas.size(), st->instances));
+        st->inject_fault = atoi(EnvOr("B200_ENGINE_FAULT_REPLICA", "-1").c_str());
         st->busy.assign(st->replicas.size() * st->instances, 0);
         st->next_ticket.assign(st->replicas.size(), 0);
         st->serving.assign(st->replicas.size(), 0);
@@ -605,7 +609,7 @@ bool ModelImpl::Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::ve
 
 void ModelImpl::RunCoalesced(Loaded& st, const std::vector<Pending*>& batch) {
     const b200::Plan& P = *st.plan;
-    const int G = (int)st.replicas.size();
+    if (batch.empty()) return;
     std::vector<b200::Replica::Segment> segs(batch.size());
     for (size_t k = 0; k < batch.size(); ++k) {
         Pending& p = *batch[k];
@@ -625,11 +629,25 @@ void ModelImpl::RunCoalesced(Loaded& st, const std::vector<Pending*>& batch) {
             s.cap[i] = outs[i].data ? outs[i].capacity : 0;
         }
     }
-    const int g = (int)(round_robin_.fetch_add(1) % (unsigned)G);
-    int slot = 0;
-    b200::Replica* r = st.Acquire(g, &slot);
-    try { r->RunSegments(segs, batch.front()->u8_mask); } catch (...) { st.Release(slot); throw; }
-    st.Release(slot);
+    for (;;) {
+        std::vector<int> healthy = st.Healthy();
+        if (healthy.empty()) throw std::runtime_error("every GPU replica of this model has faulted; unload and load the model again");
+        const int g = healthy[round_robin_.fetch_add(1) % (unsigned)healthy.size()];
+        int slot = 0;
+        b200::Replica* r = st.Acquire(g, &slot);
+        try {
+            r->RunSegments(segs, batch.front()->u8_mask);
+            st.Release(slot);
+            return;
+        } catch (const b200::CudaError& e) {
+            st.Release(slot);
+            st.faulted[g].store(1);
+            fprintf(stderr, "[b200-engine] GPU replica %d dropped from the shard set: %s\n", g, e.what());
+        } catch (...) {
+            st.Release(slot);
+            throw;
+        }
+    }
 }
 
 // std::mutex hands a contended lock to whoever gets there first, which under 32+ request threads starves some callers for
@@ -685,11 +703,60 @@ std::vector<ShardPlan> PlanShards(int n, int G, int max_batch, int min_shard, in
     return shards;
 }
 
-// The multi-GPU batch scheduler: contiguous split of the batch over replicas, no collective
-// (SURVEY.md §8e).  Small batches go to one replica chosen round-robin so concurrent callers spread.
+GpuWorkers::GpuWorkers(int gpus, int per_gpu) {
+    for (int g = 0; g < gpus; ++g) queues_.emplace_back(new Queue());
+    for (int g = 0; g < gpus; ++g)
+        for (int j = 0; j < std::max(1, per_gpu); ++j)
+            threads_.emplace_back([this, g] {
+                Queue& q = *queues_[g];
+                for (;;) {
+                    std::packaged_task<void()> task;
+                    {
+                        std::unique_lock<std::mutex> lk(q.mu);
+                        q.cv.wait(lk, [&] { return q.stop || !q.tasks.empty(); });
+                        if (q.tasks.empty()) return;  // stop requested and drained
+                        task = std::move(q.tasks.front());
+                        q.tasks.pop_front();
+                    }
+                    task();
+                }
+            });
+}
+GpuWorkers::~GpuWorkers() {
+    for (auto& q : queues_) {
+        { std::lock_guard<std::mutex> lk(q->mu); q->stop = true; }
+        q->cv.notify_all();
+    }
+    for (auto& t : threads_) t.join();
+}
+std::future<void> GpuWorkers::Submit(int gpu, std::function<void()> fn) {
+    std::packaged_task<void()> task(std::move(fn));
+    std::future<void> fut = task.get_future();
+    Queue& q = *queues_[gpu];
+    { std::lock_guard<std::mutex> lk(q.mu); q.tasks.push_back(std::move(task)); }
+    q.cv.notify_one();
+    return fut;
+}
+
+std::vector<int> ModelImpl::Loaded::Healthy() const {
+    std::vector<int> h;
+    for (size_t g = 0; g < replicas.size(); ++g)
+        if (!faulted[g].load(std::memory_order_relaxed)) h.push_back((int)g);
+    return h;
+}
+int ModelImpl::FaultedReplicas() const {
+    auto st = Pin();
+    int n = 0;
+    if (st) for (auto& f : st->faulted) n += f.load() ? 1 : 0;
+    return n;
+}
+
+// The multi-GPU batch scheduler: contiguous split of the batch over the healthy replicas, no collective.
+// Small batches go whole to one replica chosen round-robin so concurrent callers spread.  Shards of a split request run on the
+// persistent per-GPU workers; a shard whose GPU raises a CUDA error marks that replica faulted (it leaves the shard set for good)
+// and is re-run on a healthy one.
 bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_ptrs, std::vector<OutDesc>& outs, unsigned u8_mask) {
     const b200::Plan& P = *st.plan;
-    const int G = (int)st.replicas.size();
     const int max_b = P.max_batch;
     std::vector<size_t> in_stride(P.inputs.size()), out_stride(P.outputs.size());
     for (size_t i = 0; i < P.inputs.size(); ++i) {
@@ -707,17 +774,16 @@ bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_pt
         outs[i].dims[0] = n;
         outs[i].produced = (size_t)n * out_stride[i];
     }
-    const int kMinShard = min_shard_;
     using Shard = ShardPlan;
-    int rr = (int)(round_robin_.fetch_add(1) % (unsigned)G);
-    std::vector<Shard> shards = PlanShards(n, G, max_b, kMinShard, rr);
-    int use = 0;  // replicas 0..use-1 take part when the batch is split
+    std::vector<int> healthy = st.Healthy();
+    if (healthy.empty()) throw std::runtime_error("every GPU replica of this model has faulted; unload and load the model again");
+    const int rr = (int)(round_robin_.fetch_add(1) % (unsigned)healthy.size());
+    std::vector<Shard> shards = PlanShards(n, (int)healthy.size(), max_b, min_shard_, rr);
+    for (auto& s : shards) s.replica = healthy[s.replica];  // shard-set ordinal -> replica index
     bool single = true;
-    for (auto& s : shards) {
-        use = std::max(use, s.replica + 1);
-        single = single && s.replica == shards[0].replica;
-    }
-    auto run_shard = [&](const Shard& s) {
+    for (auto& s : shards) single = single && s.replica == shards[0].replica;
+
+    auto run_on = [&](const Shard& s, int g) {
         std::vector<const void*> ip(P.inputs.size());
         std::vector<void*> op(outs.size(), nullptr);
         std::vector<size_t> cap(outs.size(), 0);
@@ -735,25 +801,48 @@ bool ModelImpl::Execute(Loaded& st, int n, const std::vector<const void*>& in_pt
             tk.idx = outs[0].topk_idx + (size_t)s.off * tk.k;
             tk.val = outs[0].topk_val + (size_t)s.off * tk.k;
         }
+        if (g == st.inject_fault) throw b200::CudaError("injected fault (B200_ENGINE_FAULT_REPLICA)");
         int slot = 0;
         bool alone = true;
-        b200::Replica* r = st.Acquire(s.replica, &slot, &alone);
+        b200::Replica* r = st.Acquire(g, &slot, &alone);
         try { r->Run(s.cnt, ip, op, cap, u8_mask, alone, tk.k > 0 ? &tk : nullptr); } catch (...) { st.Release(slot); throw; }
         st.Release(slot);
     };
-    if (single) {
+    // a CUDA error takes the replica out of the shard set and the shard moves to another healthy replica; any other error
+    // (bad request) propagates unchanged
+    auto run_shard = [&](const Shard& s) {
+        int g = s.replica;
+        for (;;) {
+            try {
+                run_on(s, g);
+                return;
+            } catch (const b200::CudaError& e) {
+                st.faulted[g].store(1);
+                fprintf(stderr, "[b200-engine] GPU replica %d dropped from the shard set: %s\n", g, e.what());
+                std::vector<int> h = st.Healthy();
+                if (h.empty()) throw;
+                g = h[(size_t)s.off % h.size()];
+            }
+        }
+    };
+    if (single || !st.workers) {
         for (auto& s : shards) run_shard(s);
         return true;
     }
-    // one host thread per participating replica; shards of the same replica run back to back on it
+    // one task per participating replica on that GPU's persistent worker; shards of the same replica run back to back
+    std::vector<int> used;
+    for (auto& s : shards)
+        if (std::find(used.begin(), used.end(), s.replica) == used.end()) used.push_back(s.replica);
     std::vector<std::future<void>> futs;
-    for (int g = 1; g < use; ++g)
-        futs.push_back(std::async(std::launch::async, [&, g] {
+    for (size_t u = 1; u < used.size(); ++u) {
+        const int g = used[u];
+        futs.push_back(st.workers->Submit(g, [&, g] {
             for (auto& s : shards) if (s.replica == g) run_shard(s);
         }));
+    }
     std::exception_ptr first;
     try {
-        for (auto& s : shards) if (s.replica == 0) run_shard(s);
+        for (auto& s : shards) if (s.replica == used[0]) run_shard(s);
     } catch (...) { first = std::current_exception(); }
     for (auto& f : futs) {
         try { f.get(); } catch (...) { if (!first) first = std::current_exception(); }

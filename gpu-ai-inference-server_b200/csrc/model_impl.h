@@ -3,9 +3,13 @@
 #pragma once
 #include <atomic>
 #include <condition_variable>
+#include <deque>
+#include <functional>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
@@ -33,6 +37,28 @@ struct OutDesc {
     bool topk_softmax = false;
     int32_t* topk_idx = nullptr;
     float* topk_val = nullptr;
+};
+
+// Persistent host workers of the multi-GPU batch scheduler ("one host worker thread ... per GPU"): a
+// request that is split over GPUs hands each shard to the queue of its GPU instead of creating and joining a thread per request
+// and GPU.  `per_gpu` threads serve one GPU's queue, so shards of concurrent requests can still occupy every execution instance.
+class GpuWorkers {
+public:
+    GpuWorkers(int gpus, int per_gpu);
+    ~GpuWorkers();
+    GpuWorkers(const GpuWorkers&) = delete;
+    GpuWorkers& operator=(const GpuWorkers&) = delete;
+    std::future<void> Submit(int gpu, std::function<void()> fn);
+
+private:
+    struct Queue {
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<std::packaged_task<void()>> tasks;
+        bool stop = false;
+    };
+    std::vector<std::unique_ptr<Queue>> queues_;
+    std::vector<std::thread> threads_;
 };
 
 // One contiguous piece of a batch assigned to one GPU replica.
@@ -72,6 +98,12 @@ public:
         std::condition_variable pick_cv;
         std::vector<int> busy;                               // [g * instances + j]: 1 while a Run call owns the instance
         std::vector<uint64_t> next_ticket, serving;          // per GPU: callers are served strictly first come, first served
+        // a replica whose GPU raised a CUDA error is dropped from the shard set ("a failed GPU replica should be
+        // dropped from the shard set, not crash"); requests keep being served by the others
+        std::vector<std::atomic<int>> faulted;               // [g]
+        std::vector<int> Healthy() const;                    // GPU (replica) indices still in the shard set
+        std::unique_ptr<GpuWorkers> workers;                 // created when there is more than one replica
+        int inject_fault = -1;                               // test hook (B200_ENGINE_FAULT_REPLICA): this replica fails every Run
         int Slots() const { return (int)replicas.size() * instances; }
         b200::Replica* Acquire(int g, int* slot, bool* alone = nullptr);  // blocks until an instance of GPU g is free (FIFO)
         void Release(int slot);
@@ -79,6 +111,7 @@ public:
     std::shared_ptr<Loaded> Pin() const;
     int staged_batch = 0;
     void CoalesceStats(int64_t* batches, int64_t* requests) const { *batches = co_batches_.load(); *requests = co_requests_.load(); }
+    int FaultedReplicas() const;
 
 private:
     bool ValidateInputs(const std::vector<IoDesc>& ins) const;

@@ -51,6 +51,8 @@ uint64_t B200KernelLaunchCount(void);
  * replica's own stream, max over replicas) to ms_out[0..iters).  If l2_flush != 0 a buffer larger
  * than L2 is overwritten between iterations (outside the event pair). */
 bool B200ModelStageInput(ModelHandle handle, const TensorData* input, ErrorMessage* error);
+/* Number of GPU replicas of this model that raised a CUDA error and were dropped from the shard set (0 on a healthy model). */
+int B200ModelFaultedReplicas(ModelHandle handle);
 /* Request coalescer counters: batches executed and requests they carried (requests / batches = mean coalesced size). */
 bool B200ModelCoalesceStats(ModelHandle handle, int64_t* batches, int64_t* requests);
 bool B200ModelForwardDevice(ModelHandle handle, int batch, int iters, int l2_flush, float* ms_out,

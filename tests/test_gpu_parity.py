@@ -1,9 +1,9 @@
 """GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C-ABI exactly as the
 reference's Go binding would call it, against the CPU oracle on the same seeded inputs.
 
-Tolerances (north_star): FP32 logits within 1e-3 relative (to max|logit|) with identical top-1; BF16/FP8
-"top-5 agreement" >= 99 % on the fixed synthetic set, defined as: the oracle's top-1 class is among the
-engine's top-5 (both the set-overlap and top-1 agreement are reported and loosely gated as well)."""
+Tolerances (north_star): FP32 logits within 1e-3 relative (to max|logit|) with identical top-1; BF16/FP8 top-1 agreement and
+top-5 SET agreement on the fixed 1024-image synthetic set (gates in LOWP_GATES: >= 99 % for bf16; fp8 is reported against the
+same definitions with its own measured floor)."""
 import json
 import os
 import threading
@@ -191,6 +191,7 @@ def _agreement(ref, got):
     return {"top1": float(np.mean(ref.argmax(1) == got.argmax(1))),
             "ref_top1_in_top5": float(np.mean([r in g for r, g in zip(ref.argmax(1), g5)])),
             "top5_overlap": float(np.mean([len(set(a) & set(b)) / 5 for a, b in zip(r5, g5)])),
+            "top5_set": float(np.mean([set(a) == set(b) for a, b in zip(r5, g5)])),
             "max_rel": float(np.abs(ref - got).max() / np.abs(ref).max())}
 
 
@@ -208,18 +209,39 @@ def test_densenet_fp32_matches_golden_logits(pkg, repo_dir, monkeypatch):
     assert _agreement(g["logits_fp32"], exact)["max_rel"] < 1e-4
 
 
+# north_star: "BF16/FP8 top-5 agreement >= 99 % on a fixed synthetic image set".  Measured on the 1024-image clustered set
+# (tools/synth.clustered_images_u8) against the fp32 oracle, with the plain definitions: top-1 agreement = same argmax,
+# top-5 agreement = same SET of five classes.  The fixture's classifier is synthesised so that these margins exist at all
+# (tools/make_densenet_onnx.synthesize_classifier); max_rel is the worst logit error relative to max|logit|.
+LOWP_GATES = {"bf16": {"top1": 0.99, "top5_set": 0.99, "max_rel": 0.05},
+              "fp8": {"top1": 0.99, "top5_set": 0.97, "max_rel": 0.25}}
+
+
 @pytest.mark.parametrize("precision", ["bf16", "fp8"])
 def test_densenet_low_precision_top5_agreement(pkg, repo_dir, densenet_path, monkeypatch, precision):
-    n = 96
-    x = synth.to_model_input(synth.synthetic_images_u8(n, start=2000))
-    ref = OnnxOracle(densenet_path).run({"data_0": x})[0]
-    got = _serve(pkg, repo_dir, "densenet_onnx", {"data_0": x}, {"fc6_1": (n, 1000)}, precision, monkeypatch, max_batch=96)[0]
+    n, chunk = 1024, 128
+    monkeypatch.setenv("B200_ENGINE_PRECISION", precision)
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", str(chunk))
+    oracle = OnnxOracle(densenet_path)
+    mgr = pkg.InferenceManager(repo_dir)
+    ref, got = [], []
+    try:
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        for s0 in range(0, n, chunk):
+            x = synth.to_model_input(synth.clustered_images_u8(chunk, start=20000 + s0))
+            ref.append(oracle.run({"data_0": x})[0])
+            got.append(m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [chunk, 1000])])[0].data.copy())
+    finally:
+        mgr.shutdown()
+    ref, got = np.concatenate(ref), np.concatenate(got)
     a = _agreement(ref, got)
     print(precision, a)
+    gate = LOWP_GATES[precision]
     assert np.isfinite(got).all()
-    assert a["ref_top1_in_top5"] >= 0.99, a
-    assert a["top5_overlap"] >= (0.9 if precision == "bf16" else 0.75), a
-    assert a["max_rel"] < (0.05 if precision == "bf16" else 0.3), a
+    assert a["top1"] >= gate["top1"], a
+    assert a["top5_set"] >= gate["top5_set"], a
+    assert a["max_rel"] < gate["max_rel"], a
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "fp8"])
@@ -506,33 +528,75 @@ def test_device_queries_and_vector_add(pkg):
 
 
 def test_multi_gpu_batch_sharding_matches_single_gpu(pkg, repo_dir, monkeypatch):
-    """Replicated weights, contiguous batch split, no collective: a batch served by G replicas must give the
-    per-image results of one replica (skipped on a 1-GPU box)."""
+    """Replicated weights, contiguous batch split, no collective: a batch served by G replicas must give the per-image results
+    of one replica.  On a 1-GPU box the scheduler runs over TWO replicas of device 0 (B200_ENGINE_DEVICES=0,0): same split, same
+    persistent per-GPU workers, same join - only the silicon is shared."""
     g = pkg.get_device_count()
-    if g < 2:
-        pytest.skip("needs >= 2 GPUs")
+    multi = "all" if g >= 2 else "0,0"
+    g = max(g, 2)
     monkeypatch.setenv("B200_ENGINE_PRECISION", "bf16")
     monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "16")
     monkeypatch.setenv("B200_ENGINE_MIN_SHARD", "8")
     n = 8 * g + 3
     x = synth.to_model_input(synth.synthetic_images_u8(n, start=5000))
     outs = {}
-    for devs in ("0", "all"):
+    for devs in ("0", multi):
         monkeypatch.setenv("B200_ENGINE_DEVICES", devs)
         mgr = pkg.InferenceManager(repo_dir)
         try:
             mgr.load_model("densenet_onnx")
             m = mgr.get_model("densenet_onnx")
             outs[devs] = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [n, 1000])])[0].data.copy()
-            if devs == "all":
+            if devs == multi:
                 assert f"{g} GPU replica(s)" in m.get_metadata().description
                 # small requests rotate over replicas and still agree
                 for i in range(2 * g):
                     y = m.infer([pkg.TensorData("data_0", x[i:i + 1])], [pkg.OutputConfig("fc6_1", [1, 1000])])[0].data
                     assert np.array_equal(y, outs["0"][i:i + 1])
+                # concurrent split requests share the persistent workers
+                errs = []
+
+                def worker():
+                    y = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [n, 1000])])[0].data
+                    if not np.array_equal(y, outs["0"]):
+                        errs.append("mismatch")
+                ths = [threading.Thread(target=worker) for _ in range(4)]
+                [t.start() for t in ths]
+                [t.join() for t in ths]
+                assert not errs and m.faulted_replicas() == 0
         finally:
             mgr.shutdown()
-    assert np.array_equal(outs["0"], outs["all"])     # same kernels, same per-image arithmetic: bit-identical
+    assert np.array_equal(outs["0"], outs[multi])     # same kernels, same per-image arithmetic: bit-identical
+
+
+def test_a_faulted_replica_is_dropped_from_the_shard_set(pkg, repo_dir, monkeypatch):
+    """"a failed GPU replica should be dropped from the shard set, not crash".  Replica 1 is made to raise a
+    CUDA error on every run (test hook B200_ENGINE_FAULT_REPLICA): its shard moves to a healthy replica, the request succeeds with
+    the same results, and later requests no longer use it."""
+    g = pkg.get_device_count()
+    monkeypatch.setenv("B200_ENGINE_DEVICES", "all" if g >= 2 else "0,0")
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "bf16")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "16")
+    monkeypatch.setenv("B200_ENGINE_MIN_SHARD", "4")
+    n = 8 * max(g, 2)
+    x = synth.to_model_input(synth.synthetic_images_u8(n, start=5100))
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        want = mgr.get_model("densenet_onnx").infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [n, 1000])])[0].data.copy()
+        mgr.unload_model("densenet_onnx")
+        monkeypatch.setenv("B200_ENGINE_FAULT_REPLICA", "1")
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        assert m.faulted_replicas() == 0
+        got = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [n, 1000])])[0].data
+        assert np.array_equal(got, want) and m.faulted_replicas() == 1
+        for i in range(4):   # small requests round-robin over the remaining replicas only
+            y = m.infer([pkg.TensorData("data_0", x[i:i + 1])], [pkg.OutputConfig("fc6_1", [1, 1000])])[0].data
+            assert np.array_equal(y, want[i:i + 1])
+        assert m.faulted_replicas() == 1
+    finally:
+        mgr.shutdown()
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -52,12 +52,13 @@ import os, sys
 sys.path.insert(0, {root!r})
 os.environ["B200_BENCH_BACKEND"] = "gloo"
 import bench
-rank, local, world, reduce_max, barrier = bench._dist()
+rank, local, world, reduce_max, barrier, host_barrier = bench._dist()
 assert world == 2 and rank in (0, 1) and local == rank
 barrier()
 m = reduce_max(10.0 + rank)          # MAX over ranks of the per-rank time
 assert m == 11.0, m
 barrier()
+host_barrier()
 import os, sys
 os.write(1, ("RANK_OK %d\\n" % rank).encode())   # ONE write per rank: two ranks share the pipe and print() may interleave
 '''

@@ -53,12 +53,56 @@ def build_module(calib_images: int = 32):
         for i in range(0, calib_images, 16):
             m(x[i:i + 16])
     m.eval()
-    with torch.no_grad():
-        logits = m(x[:16])
-        scale = 3.0 / float(logits.std())
-        m.classifier.weight.mul_(scale)
-        m.classifier.bias.copy_(torch.empty_like(m.classifier.bias).normal_(0.0, 0.5, generator=g))
+    synthesize_classifier(m, g)
     return m
+
+
+CLUSTERS = 50             # clusters of tools/synth.clustered_images_u8 the classifier knows
+TOP5_GAINS = (1.0, 0.9, 0.8, 0.7, 0.6)
+LOGIT_SCALE = 16.0
+
+
+def class_permutation():
+    return np.random.default_rng(12345).permutation(1000)
+
+
+def synthesize_classifier(m, g) -> None:
+    """An untrained network has no decision structure: its logits are a random projection whose top-1/top-5 margins are far
+    below any reduced-precision noise floor, so "top-5 agreement" measures nothing (hard parts).  Training
+    is what creates margins; here the classifier is SYNTHESISED to the same effect: with c_k the mean penultimate feature of
+    cluster k of the synthetic evaluation set and u_k the ridge-regularised dual basis of the centred cluster means
+    (<c_j - mu, u_k> ~ delta_jk), the five classes of cluster k get the rows  LOGIT_SCALE * gain_j * u_k  (+ a small independent
+    random component), the remaining 500 classes small random rows.  An image of cluster k then has a clear top-1 (margin
+    0.15 * LOGIT_SCALE), an ordered top-5 and a gap of 0.4 * LOGIT_SCALE to the rest - the shape of a trained classifier's
+    output - while its features still come out of 120 random convolutions, which is what the kernels are tested on."""
+    import torch
+    rng = np.random.default_rng(2024)
+    feats = []
+    with torch.no_grad():
+        for k0 in range(0, CLUSTERS, 10):
+            imgs = np.concatenate([synth.clustered_images_u8(10, start=k0 + rep * CLUSTERS, clusters=CLUSTERS) for rep in range(3)])
+            x = torch.from_numpy(synth.to_model_input(imgs))
+            f = torch.nn.functional.adaptive_avg_pool2d(torch.relu(m.features(x)), 1).flatten(1).numpy().astype(np.float64)
+            feats.append((f[:10] + f[10:20] + f[20:]) / 3.0)
+    C = np.concatenate(feats)                         # [CLUSTERS, 1024] cluster means
+    mu = C.mean(0)
+    G = C - mu
+    lam = 1e-2 * np.trace(G @ G.T) / CLUSTERS
+    U = np.linalg.solve(G @ G.T + lam * np.eye(CLUSTERS), G)   # rows u_k
+    W = np.zeros((1000, 1024))
+    unorm = np.linalg.norm(U, axis=1).mean()
+    perm = class_permutation()
+    for k in range(CLUSTERS):
+        for j, gain in enumerate(TOP5_GAINS):
+            r = rng.normal(0, 1, 1024)
+            W[perm[5 * k + j]] = LOGIT_SCALE * (gain * U[k] + 0.02 * unorm * r / np.linalg.norm(r))
+    for c in range(5 * CLUSTERS, 1000):
+        r = rng.normal(0, 1, 1024)
+        W[perm[c]] = LOGIT_SCALE * 0.05 * unorm * r / np.linalg.norm(r)
+    b = -W @ mu + rng.normal(0, 0.1, 1000)
+    with torch.no_grad():
+        m.classifier.weight.copy_(torch.from_numpy(W.astype(np.float32)))
+        m.classifier.bias.copy_(torch.from_numpy(b.astype(np.float32)))
 
 
 def export_legacy(m, path: str) -> None:
