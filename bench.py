@@ -597,15 +597,13 @@ def main():
                 cpu1 = cpu_oracle_latency_1thread()
             except Exception as e:  # noqa: BLE001
                 cpu1 = {"error": repr(e)[:200]}
-        cfg = _workload(args, n_gpus)
-        cfg.update({"precision": args.precision,
-                    "launch": "torchrun one rank per GPU" if world > 1 else ("in-process replicas" if in_process_multi else "single process"),
-                    "e2e_requests_in_flight": E2E_CLIENTS})
+        cfg = _workload(args, n_gpus)   # identical to the reference arm's config: same workload on both arms
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp8": "fp8-e4m3 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)",
                           "fp32": "f32 (bf16x3 split operands on tcgen05, fp32 accumulate)"}[args.precision],
-                "data": "synthetic", "config": cfg,
+                "data": "synthetic", "config": cfg, "precision": args.precision,
+                "launch": "torchrun one rank per GPU" if world > 1 else ("in-process replicas" if in_process_multi else "single process"),
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x.nbytes), "d2h_bytes_per_step": int(B * 1000 * 4),
                         "steps": e2e_steps, "api": "ModelInfer (C-ABI) with pinned host buffers", "requests_in_flight": E2E_CLIENTS,

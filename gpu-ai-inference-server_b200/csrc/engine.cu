@@ -84,8 +84,9 @@ bool PinnedPool::IsPageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 void* PinnedPool::Take(size_t bytes) {
-    size_t cap = 1u << 20;
-    while (cap < bytes) cap <<= 1;
+    // size classes: 1 MiB granules up to 16 MiB, 4 MiB granules above (a power-of-two class pinned 256 MB for a 154 MB request)
+    const size_t gran = bytes <= (16u << 20) ? (1u << 20) : (4u << 20);
+    const size_t cap = std::max(gran, (bytes + gran - 1) / gran * gran);
     {
         std::lock_guard<std::mutex> lk(mu_);
         if (!budget_) {
@@ -112,6 +113,22 @@ void PinnedPool::Give(void* p) {
     std::lock_guard<std::mutex> lk(mu_);
     for (auto& b : bufs_)
         if (b.p == p) { b.used = false; return; }
+}
+// Releases every idle staging buffer (called when a model is unloaded: the pool is process-wide and would otherwise keep
+// its high-water mark pinned for the life of the process).
+void PinnedPool::Trim() {
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (size_t i = 0; i < bufs_.size();) {
+            if (bufs_[i].used) { ++i; continue; }
+            drop.push_back(bufs_[i].p);
+            total_ -= bufs_[i].cap;
+            bufs_[i] = bufs_.back();
+            bufs_.pop_back();
+        }
+    }
+    for (void* p : drop) cudaFreeHost(p);
 }
 
 Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, std::shared_ptr<ComputeChain> chain, const Replica* weights_of)
@@ -816,6 +833,7 @@ void Replica::ReadOutput(int output_index, void* host, size_t bytes) {
     std::lock_guard<std::mutex> lk(mu_);
     DeviceGuard g(device_);
     const TensorDesc& t = plan_->tensors[plan_->outputs.at(output_index)];
+    bytes = std::min(bytes, (size_t)plan_->max_batch * t.C * t.H * t.W * 4);  // never read past the output buffer
     CudaCheck(cudaMemcpyAsync(host, BufferPtr(t.buffer), bytes, cudaMemcpyDeviceToHost, stream_), "D2H read");
     CudaCheck(cudaStreamSynchronize(stream_), "read sync");
 }

@@ -42,6 +42,7 @@ public:
     static bool IsPageable(const void* p);
     void* Take(size_t bytes);  // nullptr when the budget (B200_ENGINE_STAGING_MB, default 2048) is exhausted
     void Give(void* p);
+    void Trim();               // frees every idle buffer
     ~PinnedPool();
 private:
     struct Buf { void* p; size_t cap; bool used; };

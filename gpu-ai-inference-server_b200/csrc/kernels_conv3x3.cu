@@ -12,6 +12,13 @@
 // on B200: the tensor core applies the 128-byte XOR swizzle to ABSOLUTE shared-memory address bits, exactly like
 // the TMA unit that wrote the tile, so a start address that is not a multiple of 8 rows needs no fix-up; the
 // descriptor's matrix-base-offset field must stay 0 - setting it to the row phase gives wrong results.)
+// N = 32 output channels would make every MMA A-fetch bound (4 KB of A per 16 cycles of math, measured: tensor pipe 30 % active),
+// so the three taps of one filter ROW are stacked along N: the weight tile of filter row fr is [fs*32 + o][128 B] (96 rows) and
+// ONE MMA per (fr, K step) with the A view shifted by fr*16 slots computes, for every patch slot m,
+//     D[m][fs*32 + o] += A[m + fr*16] . W(fr, fs)[o]          which is the tap's contribution to OUTPUT slot m - fs.
+// The epilogue adds the three column groups across neighbouring TMEM lanes (two warp shuffles per channel; a warp owns two
+// 16-slot patch rows, and m + 2 stays inside the row for every stored x <= 13): out[m] = D[m][0:32] + D[m+1][32:64] + D[m+2][64:96].
+// A is fetched 3x per K step instead of 9x (12 MMAs of N = 96 per 128-byte plane instead of 36 of N = 32).
 // No thread ever touches the activations: the producer
 // is one elected lane issuing TMA, so the whole CTA is 6 warps (TMA, MMA, 4 epilogue).  The 9 weight tiles
 // ([32][128 B] each) are TMA-loaded once and stay resident; patches stream through a ring of kBufs buffers.
@@ -29,7 +36,9 @@ constexpr int kC3Threads = 192;
 constexpr int kC3PW = 16;                          // patch width in slots (TW <= 14)
 constexpr int kC3PlaneBytes = 10 * kC3PW * 128;    // (TH+2 <= 10) rows x 16 slots x 128 B = 20 KB per 128-byte K plane
 constexpr int kC3BN = 32;
-constexpr int kC3Acc = 4;                          // TMEM accumulators of 32 columns
+constexpr int kC3NS = 3 * kC3BN;                   // MMA N: the three taps of a filter row stacked
+constexpr int kC3Acc = 4;                          // TMEM accumulators
+constexpr int kC3AccStride = 128;                  // columns between accumulators (96 used)
 
 template <int CPT> struct C3Cfg {                  // CPT = 128-byte K planes per pixel (1: e4m3, 2: bf16)
     static constexpr int kBufs = CPT == 1 ? 6 : 3;
@@ -85,7 +94,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         PrefetchTensorMap(&tmap_w);
         PrefetchTensorMap(&tmap_in);
     }
-    if (wrole == 1) TmemAlloc(tmem_slot, kC3Acc * kC3BN);
+    if (wrole == 1) TmemAlloc(tmem_slot, kC3Acc * kC3AccStride);
     TcFenceBefore();
     __syncthreads();
     TcFenceAfter();
@@ -96,7 +105,11 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         // =========================================================== TMA producer: weights once, then the patch ring
         if (ElectOne()) {
             MbarArriveExpectTx(w_bar, (uint32_t)Cfg::kWeightBytes);
-            for (int t = 0; t < 9 * CPT; ++t) TmaLoad2D(s_w + t * kC3BN * 128, &tmap_w, w_bar, t * ME::kChunk, 0);
+            // packed K order is (tap, plane); resident order is (filter row, plane, fs) so that the three taps of a row form one
+            // contiguous [96][128 B] tile
+            for (int tap = 0; tap < 9; ++tap)
+                for (int j = 0; j < CPT; ++j)
+                    TmaLoad2D(s_w + (((tap / 3) * CPT + j) * 3 + tap % 3) * kC3BN * 128, &tmap_w, w_bar, (tap * CPT + j) * ME::kChunk, 0);
         }
         __syncwarp();
         GridDepWait();  // the patches are the previous kernel's output
@@ -117,7 +130,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         }
     } else if (wrole == 1) {
         // =========================================================== MMA issuer
-        constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, kC3BN);
+        constexpr uint32_t idesc = MakeInstrDesc(ME::kFmt, kC3NS);
         const uint64_t b_base = MakeSmemDesc(SmemAddr(s_w));
         const uint32_t patch_addr = SmemAddr(s_patch);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -130,18 +143,18 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             MbarWait(&patch_full[buf], ph);
             TcFenceAfter();
             if (ElectOne()) {
-                const uint32_t d_addr = tmem_u + acc * kC3BN;
+                const uint32_t d_addr = tmem_u + acc * kC3AccStride;
                 const uint32_t a_buf = patch_addr + buf * Cfg::kBufBytes;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
+                for (int fr = 0; fr < 3; ++fr) {
 #pragma unroll
                     for (int j = 0; j < CPT; ++j) {
-                        // rows shifted by (fr*16 + fs) slots of 128 B
-                        const uint64_t a_desc = MakeSmemDesc(a_buf + j * kC3PlaneBytes + ((tap / 3) * kC3PW + (tap % 3)) * 128);
-                        const uint64_t b_desc = b_base + (uint64_t)((tap * CPT + j) * (kC3BN * 128 / 16));
+                        // rows shifted by fr*16 slots of 128 B; the fs shift lives in the epilogue
+                        const uint64_t a_desc = MakeSmemDesc(a_buf + j * kC3PlaneBytes + fr * kC3PW * 128);
+                        const uint64_t b_desc = b_base + (uint64_t)(((fr * CPT + j) * 3) * (kC3BN * 128 / 16));
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            if (ks < p.ksteps) UmmaSS<ME::kKind>(d_addr, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (tap | j | ks) ? 1u : 0u);
+                            if (ks < p.ksteps) UmmaSS<ME::kKind>(d_addr, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (fr | j | ks) ? 1u : 0u);
                     }
                 }
                 UmmaCommit(&patch_empty[buf]);
@@ -169,10 +182,23 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
             MbarWait(&tmem_full[acc], acc_phase);
             TcFenceAfter();
             uint32_t r[32];
-            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kC3BN, r);
-            TmemLoadWait();
-            TcFenceBefore();
-            MbarArrive(&tmem_empty[acc]);  // the accumulator is in registers: release it before the stores
+            {
+                uint32_t r1[32], r2[32];
+                const uint32_t t_addr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * kC3AccStride;
+                TmemLoad32(t_addr, r);
+                TmemLoad32(t_addr + 32, r1);
+                TmemLoad32(t_addr + 64, r2);
+                TmemLoadWait();
+                TcFenceBefore();
+                MbarArrive(&tmem_empty[acc]);  // the accumulator is in registers: release it before the math and the stores
+                // out[m] = D[m][fs = 0] + D[m + 1][fs = 1] + D[m + 2][fs = 2]  (lanes 14, 15 of a 16-slot row are never stored)
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[c]), 1);
+                    const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 2);
+                    r[c] = __float_as_uint((__uint_as_float(r[c]) + a1) + a2);
+                }
+            }
             const int oy = ty * p.TH + y, ox = tx * p.TW + x;
             if (y < p.TH && x < p.TW && oy < p.H && ox < p.W) {
                 constexpr int kWords = 32 * (int)sizeof(OutT) / 4;
@@ -192,7 +218,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     __syncthreads();
     if (wrole == 1) {
         TcFenceAfter();
-        TmemDealloc(tmem_base, kC3Acc * kC3BN);
+        TmemDealloc(tmem_base, kC3Acc * kC3AccStride);
     }
 }
 

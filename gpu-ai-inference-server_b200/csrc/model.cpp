@@ -355,6 +355,7 @@ void ModelImpl::Unload() {
     }
     loaded_.store(false, std::memory_order_release);
     memory_bytes_.store(0);
+    if (old) b200::PinnedPool::Get().Trim();
     // `old` (replicas, arenas) is released here unless an in-flight Infer still pins it.
 }
 
@@ -487,7 +488,9 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
             std::vector<void*> bufs;
             ~Staged() { for (void* b : bufs) b200::PinnedPool::Get().Give(b); }
         } staged;
-        if (stage_pageable_)
+        if (stage_pageable_) {
+            // the pointer query below must not create a primary context on a device this model does not use
+            cudaSetDevice(st->replicas[0]->device());
             for (size_t gi = 0; gi < ptrs.size(); ++gi) {
                 const auto& gd = P.input_dims[gi];
                 size_t bytes = (size_t)n * (((u8_mask >> gi) & 1u) ? 1 : 4);
@@ -513,6 +516,7 @@ bool ModelImpl::InferBorrowed(const std::vector<IoDesc>& ins, std::vector<OutDes
                 }
                 ptrs[gi] = pin;
             }
+        }
         const bool wants_topk = !outs.empty() && outs[0].topk > 0;  // top-k requests carry their own result arrays: not coalesced
         if (coalesce_us_ > 0 && n <= coalesce_small_ && n < P.max_batch && !wants_topk) ok = Coalesce(st, (int)n, ptrs, outs, u8_mask);
         else ok = Execute(*st, (int)n, ptrs, outs, u8_mask);
@@ -562,20 +566,36 @@ bool ModelImpl::Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::ve
         // grows to whatever arrives during one forward, when idle a request only ever waits its window
         const int G = 2 * (int)st->replicas.size();  // per GPU: one batch computing, one copying
         while (co_inflight_ >= G && queued() < cap) co_cv_.wait_for(lk, std::chrono::microseconds(100));
-        // close the batch: queue order, same input kind as the first request, total <= cap
+        // close the batch: queue order, same input kind as the first request, total <= cap.  The leader's own request is always
+        // in it: a leader is either the front of the queue (fresh quiet period) or was promoted as the front of what was left,
+        // and a single request never exceeds cap (checked by the caller).
         std::vector<Pending*> batch, rest;
         int total = 0;
-        for (auto* p : co_queue_) {
-            if (p->u8_mask == co_queue_.front()->u8_mask && total + p->n <= cap) { batch.push_back(p); total += p->n; }
-            else rest.push_back(p);
+        try {
+            for (auto* p : co_queue_) {
+                if (p->u8_mask == co_queue_.front()->u8_mask && total + p->n <= cap) { batch.push_back(p); total += p->n; }
+                else rest.push_back(p);
+            }
+        } catch (...) {  // bad_alloc while forming the batch: nobody may be left waiting for a leader that is gone
+            for (auto* p : co_queue_)
+                if (p != &me) { p->ok = false; p->err = "ONNX inference error: out of memory while batching requests"; p->done = true; p->cv.notify_one(); }
+            co_queue_.clear();
+            co_leader_ = false;
+            throw;
+        }
+        if (std::find(batch.begin(), batch.end(), &me) == batch.end()) {
+            // cannot happen (see above); if it ever does, run my request alone rather than lead an empty batch
+            batch.clear();
+            rest.clear();
+            for (auto* p : co_queue_) (p == &me ? batch : rest).push_back(p);
         }
         co_queue_.swap(rest);
         co_leader_ = false;
-        const bool mine = std::find(batch.begin(), batch.end(), &me) != batch.end();
-        if (!co_queue_.empty()) {
-            // somebody else must lead what is left (possibly me, if my request did not fit)
-            Pending* next = mine ? co_queue_.front() : &me;
-            if (next != &me) { co_leader_ = true; next->promoted = true; next->cv.notify_one(); }
+        if (!co_queue_.empty()) {  // somebody else must lead what is left
+            Pending* next = co_queue_.front();
+            co_leader_ = true;
+            next->promoted = true;
+            next->cv.notify_one();
         }
         ++co_inflight_;
         lk.unlock();
@@ -597,13 +617,8 @@ bool ModelImpl::Coalesce(const std::shared_ptr<Loaded>& st, int n, const std::ve
             p->ok = ok; p->err = err; p->done = true;
             p->cv.notify_one();
         }
-        if (mine) {
-            if (!ok) SetLastError(err);
-            return ok;
-        }
-        // my own request is still queued (it did not fit): lead the next batch right away
-        waited = true;
-        lead = true;
+        if (!ok) SetLastError(err);
+        return ok;
     }
 }
 

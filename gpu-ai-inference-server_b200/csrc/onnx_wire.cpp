@@ -53,6 +53,13 @@ struct Reader {
         p += 4;
         return f;
     }
+    double Fixed64d() {
+        Need(8);
+        double d;
+        memcpy(&d, p, 8);
+        p += 8;
+        return d;
+    }
     std::string Str() {
         Reader r = Sub();
         return std::string((const char*)r.p, (size_t)(r.end - r.p));
@@ -106,6 +113,7 @@ TensorConst ParseTensor(Reader r) {
     const uint8_t* raw = nullptr;
     size_t raw_n = 0;
     std::vector<float> fl;
+    std::vector<double> dbl;
     std::vector<int64_t> i32, i64;
     while (!r.Done()) {
         uint64_t key = r.Varint();
@@ -116,6 +124,16 @@ TensorConst ParseTensor(Reader r) {
             case 4: ReadFloats(r, wt, fl); break;
             case 5: ReadInts(r, wt, i32); break;
             case 7: ReadInts(r, wt, i64); break;
+            case 10:  // double_data: repeated fixed64, packed or not
+                if (wt == 1) {
+                    dbl.push_back(r.Fixed64d());
+                } else if (wt == 2) {
+                    Reader s = r.Sub();
+                    while (!s.Done()) dbl.push_back(s.Fixed64d());
+                } else {
+                    r.Skip(wt);
+                }
+                break;
             case 8: t.name = r.Str(); break;
             case 9: {
                 Reader s = r.Sub();
@@ -133,7 +151,12 @@ TensorConst ParseTensor(Reader r) {
             default: r.Skip(wt);
         }
     }
-    size_t n = t.NumElements();
+    size_t n = 1;
+    for (int64_t d : t.dims) {
+        if (d < 0) throw std::runtime_error("onnx: tensor " + t.name + " has a negative dimension");
+        if (d != 0 && n > (size_t)1 << 40) throw std::runtime_error("onnx: tensor " + t.name + " is implausibly large");
+        n *= (size_t)d;
+    }
     auto need = [&](size_t esz) {
         if (raw_n != n * esz) throw std::runtime_error("onnx: raw_data size mismatch for tensor " + t.name);
     };
@@ -146,6 +169,9 @@ TensorConst ParseTensor(Reader r) {
             if (raw) {
                 need(8); t.f32.resize(n);
                 for (size_t i = 0; i < n; ++i) { double d; memcpy(&d, raw + 8 * i, 8); t.f32[i] = (float)d; }
+            } else {
+                t.f32.resize(dbl.size());
+                for (size_t i = 0; i < dbl.size(); ++i) t.f32[i] = (float)dbl[i];
             }
             break;
         case kFloat16:
@@ -168,7 +194,10 @@ TensorConst ParseTensor(Reader r) {
         default:
             throw std::runtime_error("onnx: unsupported tensor data type " + std::to_string(t.dtype));
     }
-    if (!t.f32.empty() && t.f32.size() != n) throw std::runtime_error("onnx: element count mismatch for tensor " + t.name);
+    // every tensor must carry exactly the elements its dims announce (an empty payload for n > 0 used to slip through and
+    // was indexed later)
+    const bool is_float = t.dtype == kFloat || t.dtype == kDouble || t.dtype == kFloat16;
+    if ((is_float ? t.f32.size() : t.i64.size()) != n) throw std::runtime_error("onnx: element count mismatch for tensor " + t.name);
     return t;
 }
 

@@ -89,7 +89,40 @@ public:
         act_dtype_ = prec == Precision::FP32 ? DType::F32 : prec == Precision::BF16 ? DType::BF16 : DType::FP8;
     }
 
+    // Malformed or unusual files must fail Load() with a message, never index out of bounds: operand counts per operator,
+    // graph inputs with a usable shape, initializers whose element count matches their dims (onnx_wire.cpp checks the latter).
+    void ValidateGraph() {
+        static const std::unordered_map<std::string, std::pair<int, int>> arity = {
+            {"Conv", {2, 3}}, {"BatchNormalization", {5, 5}}, {"Gemm", {2, 3}}, {"MatMul", {2, 2}}, {"Add", {2, 2}},
+            {"Relu", {1, 1}}, {"Softmax", {1, 1}}, {"MaxPool", {1, 1}}, {"AveragePool", {1, 1}}, {"GlobalAveragePool", {1, 1}},
+            {"Flatten", {1, 1}}, {"Identity", {1, 1}}, {"Dropout", {1, 3}}, {"Concat", {1, 1 << 20}}};
+        for (const auto& n : g_.nodes) {
+            auto it = arity.find(n.op_type);
+            if (it == arity.end()) continue;  // unsupported operators are reported by name during lowering
+            const int ni = (int)n.inputs.size();
+            if (ni < it->second.first || ni > it->second.second)
+                Fail(n.op_type + " node '" + (n.name.empty() && !n.outputs.empty() ? n.outputs[0] : n.name) + "' has " + std::to_string(ni) +
+                     " inputs");
+            if (n.outputs.empty()) Fail(n.op_type + " node '" + n.name + "' has no outputs");
+            for (int k = 0; k < it->second.first; ++k)
+                if (n.inputs[k].empty()) Fail(n.op_type + " node '" + n.name + "' omits required input " + std::to_string(k));
+        }
+        for (const auto& vi : g_.inputs) {
+            if (vi.dims.empty()) Fail("graph input '" + vi.name + "' has no shape (rank 0 inputs are not supported)");
+            for (size_t k = 1; k < vi.dims.size(); ++k)
+                if (vi.dims[k] <= 0) Fail("graph input '" + vi.name + "' has an unknown or non-positive dimension " + std::to_string(k));
+        }
+        for (const auto& kv : g_.initializers) {
+            const auto& t = kv.second;
+            const size_t n = t.NumElements();
+            if (!t.f32.empty() && t.f32.size() != n) Fail("initializer '" + kv.first + "': element count does not match its dims");
+            if (!t.i64.empty() && t.i64.size() != n) Fail("initializer '" + kv.first + "': element count does not match its dims");
+            if (t.f32.empty() && t.i64.empty() && n != 0) Fail("initializer '" + kv.first + "' carries no data");
+        }
+    }
+
     Plan Run() {
+        ValidateGraph();
         BuildAliasesAndConsumers();
         InferShapes();
         PlanConcatGroups();

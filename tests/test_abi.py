@@ -190,3 +190,44 @@ def test_native_replay_tool_links_against_the_c_abi_only(tmp_path):
     r = subprocess.run([exe, "--repo", str(tmp_path), "--requests", "1", "--threads", "1"], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0
     assert "load failed" in r.stderr or "ModelInfer" in r.stderr or r.returncode == 1
+
+
+def test_importer_rejects_malformed_models_with_a_message(pkg, tmp_path):
+    """Unusual or malformed files must fail Load() with a message instead of undefined behaviour: a graph
+    input without a shape, an initializer without a payload, wrong operand counts; DOUBLE tensors in `double_data` are read."""
+    import struct
+    import numpy as np
+    from tools import onnx_lite as ol
+
+    def write(name, graph_bytes):
+        d = tmp_path / name
+        os.makedirs(d, exist_ok=True)
+        blob = ol._w_int(1, 7) + ol._w_bytes(7, graph_bytes) + ol._w_bytes(8, ol._w_str(1, "") + ol._w_int(2, 12))
+        with open(d / "model.onnx", "wb") as fh:
+            fh.write(blob)
+        return str(d)
+
+    vi = lambda name, shape: ol._ser_value_info(ol.ValueInfo(name, ol.FLOAT, shape))  # noqa: E731
+    matmul = ol._w_bytes(1, ol._ser_node(ol.Node("MatMul", ["x", "w"], ["y"])))
+    w_ok = ol._w_bytes(5, ol._ser_tensor("w", np.ones((3, 2), np.float32)))
+    # (1) graph input with no shape at all
+    no_shape = ol._w_str(1, "x") + ol._w_bytes(2, ol._w_bytes(1, ol._w_int(1, ol.FLOAT)))
+    with pytest.raises(pkg.EngineError, match="has no shape"):
+        pkg.plan_describe(write("noshape", matmul + w_ok + ol._w_bytes(11, no_shape) + ol._w_bytes(12, vi("y", ["N", 2]))), "fp32", 1)
+    # (2) FLOAT initializer that announces 3x2 elements and carries none
+    w_empty = ol._w_bytes(5, ol._w_int(1, 3) + ol._w_int(1, 2) + ol._w_int(2, ol.FLOAT) + ol._w_str(8, "w"))
+    with pytest.raises(pkg.EngineError, match="element count mismatch for tensor w"):
+        pkg.plan_describe(write("empty", matmul + w_empty + ol._w_bytes(11, vi("x", ["N", 3])) + ol._w_bytes(12, vi("y", ["N", 2]))), "fp32", 1)
+    # (3) negative dimension
+    w_neg = ol._w_bytes(5, ol._w_int(1, 3) + ol._w_key(1, 0) + ol._w_varint((1 << 64) - 2) + ol._w_int(2, ol.FLOAT) + ol._w_str(8, "w"))
+    with pytest.raises(pkg.EngineError, match="negative dimension"):
+        pkg.plan_describe(write("neg", matmul + w_neg + ol._w_bytes(11, vi("x", ["N", 3])) + ol._w_bytes(12, vi("y", ["N", 2]))), "fp32", 1)
+    # (4) BatchNormalization with two operands
+    bn = ol._w_bytes(1, ol._ser_node(ol.Node("BatchNormalization", ["x", "w"], ["y"])))
+    with pytest.raises(pkg.EngineError, match="BatchNormalization node .* has 2 inputs"):
+        pkg.plan_describe(write("bn2", bn + w_ok + ol._w_bytes(11, vi("x", ["N", 3, 4, 4])) + ol._w_bytes(12, vi("y", ["N", 3, 4, 4]))), "fp32", 1)
+    # (5) DOUBLE weights stored in double_data (field 10, packed) are converted, not dropped
+    dbl = b"".join(struct.pack("<d", float(v)) for v in range(6))
+    w_dbl = ol._w_bytes(5, ol._w_int(1, 3) + ol._w_int(1, 2) + ol._w_int(2, 11) + ol._w_str(8, "w") + ol._w_bytes(10, dbl))
+    d = pkg.plan_describe(write("dbl", matmul + w_dbl + ol._w_bytes(11, vi("x", ["N", 3])) + ol._w_bytes(12, vi("y", ["N", 2]))), "fp32", 1)
+    assert [s["kind"] for s in d["steps"]] == ["conv"] and d["steps"][0]["Cin"] == 3 and d["steps"][0]["Cout"] == 2

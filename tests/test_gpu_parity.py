@@ -203,7 +203,7 @@ def test_densenet_fp32_matches_golden_logits(pkg, repo_dir, monkeypatch):
     a = _agreement(g["logits_fp64"], got)
     print("fp32 (tcgen05, bf16-split operands) vs fp64 golden:", a)
     assert a["max_rel"] < 1e-3 and a["top1"] == 1.0, a          # north_star fp32 gate
-    assert a["max_rel"] < 2e-4, a                                # what three bf16 products per term deliver (simulated 4e-5)
+    assert a["max_rel"] < 5e-4, a                                # three bf16 products per term deliver ~1e-4 (simulated 4e-5 .. 1.2e-4)
     monkeypatch.setenv("B200_ENGINE_FP32_EXACT", "1")            # the exact FFMA kernels: fp32-reassociation noise only
     exact = _serve(pkg, repo_dir, "densenet_onnx", {"data_0": x}, {"fc6_1": (n, 1000)}, "fp32", monkeypatch)[0]
     assert _agreement(g["logits_fp32"], exact)["max_rel"] < 1e-4
@@ -214,7 +214,7 @@ def test_densenet_fp32_matches_golden_logits(pkg, repo_dir, monkeypatch):
 # top-5 agreement = same SET of five classes.  The fixture's classifier is synthesised so that these margins exist at all
 # (tools/make_densenet_onnx.synthesize_classifier); max_rel is the worst logit error relative to max|logit|.
 LOWP_GATES = {"bf16": {"top1": 0.99, "top5_set": 0.99, "max_rel": 0.05},
-              "fp8": {"top1": 0.99, "top5_set": 0.97, "max_rel": 0.25}}
+              "fp8": {"top1": 0.99, "top5_set": 0.98, "max_rel": 0.25}}   # measured: top-1 100 %, top-5 set 99.0 %, max_rel 0.157
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp8"])
@@ -685,3 +685,81 @@ def test_on_device_softmax_top5_matches_a_host_sort(pkg, repo_dir, monkeypatch):
             m.infer_topk([pkg.TensorData("data_0", x)], k=65)
     finally:
         mgr.shutdown()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Exact-arithmetic cases: operands chosen so that every product, every partial sum and every stored value is representable
+# in e4m3 (small multiples of 0.5, per-channel weight scales that are powers of two times 1/448).  Reduced precision then
+# loses nothing, so ALL THREE modes must reproduce the fp32 oracle BIT FOR BIT - a mis-indexed K-tail column, a wrong tap
+# shift, a swapped swizzle piece or a dropped split term shows up as a hard mismatch instead of hiding inside a tolerance.
+def _unit_bn(c, prefix):
+    # scale = gamma / sqrt(var + eps) == 1.0 and shift == 0 after rounding to fp32/f16/bf16
+    return {prefix + ".g": np.ones(c), prefix + ".b": np.zeros(c), prefix + ".m": np.zeros(c), prefix + ".v": np.full(c, 1.0 - 1e-5)}
+
+
+def _exact_case(case, tmp_path, rng):
+    if case.startswith("conv1x1_"):
+        cin, cout, hw = int(case.split("_")[1]), 128, 9
+        w = np.zeros((cout, cin, 1, 1))
+        for c in range(cin):                               # every input channel feeds exactly one output channel
+            w[c % cout, c, 0, 0] = rng.choice([-1.0, -0.5, 0.5, 1.0])
+        inits = {**_unit_bn(cin, "bn"), "w": w, "b": rng.choice([-0.5, 0.0, 0.5], cout)}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1, bias="b"),
+                 onnx_lite.Node("Relu", ["c"], ["y"])]
+        x = np.zeros((3, cin, hw, hw), np.float32)
+        for n in range(3):                                 # two non-zero channels per pixel, in different residue classes mod 128
+            for y in range(hw):
+                for xx in range(hw):
+                    c0 = int(rng.integers(0, cin))
+                    c1 = (c0 + 1 + int(rng.integers(0, min(cin, cout) - 1))) % cin
+                    if c1 % cout == c0 % cout:
+                        c1 = (c1 + 1) % cin
+                    x[n, c0, y, xx] = rng.choice([1.0, 2.0])
+                    x[n, c1, y, xx] = rng.choice([-2.0, 1.0, 2.0])   # negative: removed by the prologue ReLU
+        shp, out = (cin, hw, hw), (cout, hw, hw)
+    elif case == "conv3x3":
+        cin, cout, hw = 128, 32, 14
+        w = np.zeros((cout, cin, 3, 3))
+        for c in range(cin):
+            for t in range(9):
+                w[c % cout, c, t // 3, t % 3] = rng.choice([-1.0, -0.5, 0.5, 1.0])
+        inits = {"w": w}
+        nodes = [_conv_node("x", "w", "y", 3, 1, 1)]
+        x = np.zeros((3, cin, hw, hw), np.float32)
+        for n in range(3):                                 # one non-zero channel per pixel; the 9 neighbours of any output pixel
+            for y in range(hw):                            # carry 9 different channels (base + 3*dy + dx) -> <= 1 product per output
+                for xx in range(hw):
+                    x[n, (17 * n + 3 * y + xx) % cin, y, xx] = rng.choice([1.0, 2.0])
+        shp, out = (cin, hw, hw), (cout, hw, hw)
+    elif case == "transition":
+        cin, cout, hw = 256, 128, 14
+        w = np.zeros((cout, cin, 1, 1))
+        for c in range(cin):
+            w[c % cout, c, 0, 0] = rng.choice([-1.0, 1.0])
+        inits = {**_unit_bn(cin, "bn"), "w": w}
+        nodes = [_bn_node("x", "bn", "n"), onnx_lite.Node("Relu", ["n"], ["r"]), _conv_node("r", "w", "c", 1),
+                 onnx_lite.Node("AveragePool", ["c"], ["y"], {"kernel_shape": [2, 2], "strides": [2, 2], "pads": [0, 0, 0, 0]})]
+        x = np.zeros((3, cin, hw, hw), np.float32)
+        for n in range(3):                                 # eight channels per 2x2 window (distinct mod 128), values 0 / 4 -> averages 0..4
+            for y in range(hw):
+                for xx in range(hw):
+                    for k in range(8):
+                        x[n, (5 * n + 7 * (y // 2) + (xx // 2) + 16 * k) % cin, y, xx] = rng.choice([0.0, 4.0])
+        shp, out = (cin, hw, hw), (cout, hw // 2, hw // 2)
+    else:
+        raise KeyError(case)
+    path = _graph_case(tmp_path, "exact_" + case, nodes, inits, shp, "y", out)
+    return path, "exact_" + case, x, out
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp8"])
+@pytest.mark.parametrize("case", ["conv1x1_64", "conv1x1_96", "conv1x1_352", "conv1x1_608", "conv1x1_1024", "conv3x3", "transition"])
+def test_exactly_representable_operands_give_bit_identical_results(pkg, tmp_path, monkeypatch, case, precision):
+    rng = np.random.default_rng(abs(hash("exact" + case)) % 2**31)
+    path, name, x, out = _exact_case(case, tmp_path, rng)
+    want = OnnxOracle(path).run({"x": x})[0]
+    assert np.abs(want).max() <= 7.5 and np.array_equal(want, np.round(want * 4) / 4) and np.count_nonzero(want) > want.size // 50
+    got = _serve(pkg, str(tmp_path), name, {"x": x}, {"y": (len(x),) + tuple(out)}, precision, monkeypatch)[0]
+    bad = np.argwhere(got != want)
+    assert len(bad) == 0, f"{case}/{precision}: {len(bad)} of {want.size} elements differ, first at {bad[:4].tolist()}: " \
+                          f"{got[tuple(bad[0])]} vs {want[tuple(bad[0])]}"
