@@ -225,8 +225,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
         if (pr.use_f32x3) {
             // [Cout_pad][R*S*Cin*2] bf16: per filter tap and 32 input channels one 128-byte row [w0 x32 | w1 x32], w = w0 + w1
             const int bn = kernels::F32x3TileN(a_eff);
-            const bool stacked = kernels::F32x3StackedN(a_eff);  // residual terms in rows o + 32 instead of 32 elements further
-            const int cout_pad = stacked ? bn : (s.Cout + bn - 1) / bn * bn;
+            const int cout_pad = kernels::F32x3PackedRows(a_eff);
             const int K_pad = kernels::F32x3PackedK(a_eff);
             std::vector<uint16_t> packed((size_t)cout_pad * K_pad, 0);
             for (int o = 0; o < s.Cout; ++o)
@@ -237,9 +236,11 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
                         const uint32_t u0 = (uint32_t)h0 << 16;
                         float f0;
                         memcpy(&f0, &u0, 4);
-                        const size_t idx = (size_t)o * K_pad + kernels::F32x3WeightIndex(a_eff, tap, c);
-                        packed[idx] = h0;
-                        packed[stacked ? idx + (size_t)32 * K_pad : idx + 32] = F32ToBf16(v - f0);
+                        int row, col;
+                        kernels::F32x3WeightPos(a_eff, o, tap, c, 0, &row, &col);
+                        packed[(size_t)row * K_pad + col] = h0;
+                        kernels::F32x3WeightPos(a_eff, o, tap, c, 1, &row, &col);
+                        packed[(size_t)row * K_pad + col] = F32ToBf16(v - f0);
                     }
             std::vector<float> ones(s.Cout, 1.f);
             pr.umma.w = Upload(packed.data(), packed.size() * 2);

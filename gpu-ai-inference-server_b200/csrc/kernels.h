@@ -71,13 +71,13 @@ bool StemNchwSupported(const ConvArgs& a);
 
 // ---- FP32 mode on tcgen05: fp32 activations in HBM, operands split into two bf16 terms on the fly, three MMAs per product
 // (kernels_f32x3.cu).  1x1/s1 (Cin, Cout multiples of 32) and 3x3/s1/p1 (Cin multiple of 32, Cout <= 32).
-// `w.tensor_map` covers bf16 weights packed [Cout_pad][F32x3PackedK()] with F32x3WeightIndex(), box {64, F32x3TileN()}; the
-// residual term w1 = bf16(w - w0) sits 32 elements after w0 (1x1) or, when F32x3StackedN(), in row o + 32 at the same index.
+// `w.tensor_map` covers bf16 weights packed [F32x3PackedRows()][F32x3PackedK()], every weight as two terms w0 = bf16(w),
+// w1 = bf16(w - w0) placed by F32x3WeightPos(); TMA box {64, F32x3TileN()}.
 bool ConvF32x3Supported(const ConvArgs& a);
 int F32x3TileN(const ConvArgs& a);
-bool F32x3StackedN(const ConvArgs& a);
+int F32x3PackedRows(const ConvArgs& a);
 int F32x3PackedK(const ConvArgs& a);
-int F32x3WeightIndex(const ConvArgs& a, int tap, int c);
+void F32x3WeightPos(const ConvArgs& a, int o, int tap, int c, int term, int* row, int* col);
 cudaError_t ConvF32x3(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream);
 
 // 3x3/s1/p1 conv of a 128-byte-per-pixel bottleneck into <= 32 channels, patches loaded by 4-D TMA (kernels_conv3x3.cu)

@@ -342,23 +342,27 @@ cudaError_t LaunchFsL1(const CUtensorMap& tw, const CUtensorMap& tin, const CUte
 // taps), but a pixel is Cin*4 bytes, so the K dimension is walked in 32-channel PLANES: a pipeline stage = one plane of the
 // patch ((TH+2) x 16 slots x 128 B), split in place by the transform warps.  All weights stay resident (144 KB for Cin = 128).
 //
-// N = 32 output channels makes every MMA A-fetch bound (4 KB of A per 16 cycles of math), so the three products per term are
-// issued as TWO A fetches instead of three: the weight tile stacks [w0 ; w1] along N (64 rows: rows 0-31 the leading terms,
-// rows 32-63 the residuals of the same 32 output channels) and
-//     a0 x [w0 ; w1]  (N = 64)  ->  columns 0-31 += a0*w0, columns 32-63 += a0*w1
-//     a1 x  w0        (N = 32)  ->  columns 0-31 += a1*w0
-// the epilogue adds the two column halves.  A weight tile row is 128 B = two planes of one tap ([plane 2p | plane 2p+1]),
-// so the resident set is [tap][plane pair][64 rows][128 B].
+// N = 32 output channels would make every MMA A-fetch bound (4 KB of A per 16 cycles of math), so both the split terms and the
+// three taps of a filter ROW are stacked along N.  The resident weight tile of (filter row fr, plane pair) has 192 rows:
+//     rows   0.. 95:  w0 of taps (fr, 0), (fr, 1), (fr, 2)   [fs*32 + o]
+//     rows  96..191:  w1 of the same taps                      [96 + fs*32 + o]
+// and per K step two MMAs run with the A view shifted by fr*16 slots (the fs shift moves into the epilogue, see kernels_conv3x3.cu):
+//     a0 x rows 0..191 (N = 192)  ->  columns fs*32+o += a0*w0,  columns 96+fs*32+o += a0*w1
+//     a1 x rows 0.. 95 (N =  96)  ->  columns fs*32+o += a1*w0
+// i.e. 2 A fetches per (filter row, K step) instead of 9 x 3 = 27 single products.  The epilogue computes
+//     out[m][o] = sum over fs of ( D[m + fs][fs*32 + o] + D[m + fs][96 + fs*32 + o] )       (warp shuffles across TMEM lanes)
+// A weight tile row is 128 B = two planes of one tap ([plane 2p | plane 2p+1]).
 constexpr int kF3Threads = 32 * 14;   // 8 transform + 4 epilogue + TMA + MMA
 constexpr int kF3XfWarps = 8;
 constexpr int kF3PW = 16;
 constexpr int kF3PatchBytes = 10 * kF3PW * 128;
-constexpr int kF3WTile = 64 * 128;                         // one (tap, plane pair) weight tile
-constexpr int kF3Acc = 4;
-constexpr int kF3AccCols = 64;
+constexpr int kF3WRows = 192;
+constexpr int kF3WTile = kF3WRows * 128;                   // one (filter row, plane pair) weight tile
+constexpr int kF3Acc = 2;
+constexpr int kF3AccCols = 256;                            // column stride between accumulators (192 used)
 constexpr int kF3MaxPlanes = 4;                            // Cin <= 128
 constexpr int kF3Stages = 4;
-constexpr int kF3ResBytes = 9 * (kF3MaxPlanes / 2) * kF3WTile;
+constexpr int kF3ResBytes = 3 * (kF3MaxPlanes / 2) * kF3WTile;
 constexpr int kF3SmemBytes = 1024 + kF3ResBytes + kF3Stages * kF3PatchBytes + 1024 /*junk-row overreach*/ + 512;
 
 struct FsC3Params {
@@ -422,8 +426,8 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     if (wrole == 0) {
         // =========================================================== TMA producer: resident weights, then (tile, plane) stages
         if (ElectOne()) {  // the weights do not depend on the previous kernel: load them before the dependency wait
-            MbarArriveExpectTx(w_bar, (uint32_t)(9 * npairs * kF3WTile));
-            for (int t = 0; t < 9 * npairs; ++t) TmaLoad2D(s_w + t * kF3WTile, &tmap_w, w_bar, t * 64, 0);
+            MbarArriveExpectTx(w_bar, (uint32_t)(3 * npairs * kF3WTile));
+            for (int t = 0; t < 3 * npairs; ++t) TmaLoad2D(s_w + t * kF3WTile, &tmap_w, w_bar, t * 64, 0);
         }
         __syncwarp();
         GridDepWait();
@@ -444,7 +448,7 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         }
     } else if (wrole == 1) {
         // =========================================================== MMA issuer
-        constexpr uint32_t idesc64 = MakeInstrDesc(1 /*BF16*/, 64), idesc32 = MakeInstrDesc(1, 32);
+        constexpr uint32_t idesc192 = MakeInstrDesc(1 /*BF16*/, 192), idesc96 = MakeInstrDesc(1, 96);
         const uint32_t smem_u = SmemAddr(smem), w_u = SmemAddr(s_w);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         MbarWaitWarp(w_bar, 0);
@@ -460,15 +464,15 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                 TcFenceAfter();
                 if (ElectOne()) {
                     const uint32_t a_buf = smem_u + stage * kF3PatchBytes;
-                    const uint32_t b_plane = w_u + (j >> 1) * kF3WTile + (j & 1) * 64;  // this plane's 64-byte half of the pair tile
+                    const uint32_t b_plane = w_u + (j >> 1) * kF3WTile + (j & 1) * 64;  // this plane's 64-byte half of the pair tiles
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint64_t a_desc = MakeSmemDesc(a_buf + ((tap / 3) * kF3PW + (tap % 3)) * 128);
-                        const uint64_t b_desc = MakeSmemDesc(b_plane + tap * npairs * kF3WTile);
-                        UmmaSS<0>(d_addr, a_desc + 0, b_desc + 0, idesc64, (j | tap) ? 1u : 0u);  // a0 x [w0 ; w1]
-                        UmmaSS<0>(d_addr, a_desc + 2, b_desc + 2, idesc64, 1u);
-                        UmmaSS<0>(d_addr, a_desc + 4, b_desc + 0, idesc32, 1u);                   // a1 x w0
-                        UmmaSS<0>(d_addr, a_desc + 6, b_desc + 2, idesc32, 1u);
+                    for (int fr = 0; fr < 3; ++fr) {
+                        const uint64_t a_desc = MakeSmemDesc(a_buf + fr * kF3PW * 128);
+                        const uint64_t b_desc = MakeSmemDesc(b_plane + fr * npairs * kF3WTile);
+                        UmmaSS<0>(d_addr, a_desc + 0, b_desc + 0, idesc192, (j | fr) ? 1u : 0u);  // a0 x [w0 ; w1] of three taps
+                        UmmaSS<0>(d_addr, a_desc + 2, b_desc + 2, idesc192, 1u);
+                        UmmaSS<0>(d_addr, a_desc + 4, b_desc + 0, idesc96, 1u);                   // a1 x w0 of three taps
+                        UmmaSS<0>(d_addr, a_desc + 6, b_desc + 2, idesc96, 1u);
                     }
                     UmmaCommit(&empty_bar[stage]);
                     if (j == p.planes - 1) UmmaCommit(&tmem_full[acc]);
@@ -511,10 +515,23 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
             MbarWaitWarp(&tmem_full[acc], acc_phase);
             TcFenceAfter();
-            uint32_t r[32], r1[32];
-            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kF3AccCols, r);
-            TmemLoad32(tmem_base + ((uint32_t)(e * 32) << 16) + acc * kF3AccCols + 32, r1);
-            TmemLoadWait();
+            float r[32];
+            {
+                const uint32_t t_addr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * kF3AccCols;
+#pragma unroll
+                for (int fs = 0; fs < 3; ++fs) {   // out[m] += (D[m + fs][fs*32 + o] + D[m + fs][96 + fs*32 + o])
+                    uint32_t t0[32], t1[32];
+                    TmemLoad32(t_addr + fs * 32, t0);
+                    TmemLoad32(t_addr + 96 + fs * 32, t1);
+                    TmemLoadWait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        float v = __uint_as_float(t0[c]) + __uint_as_float(t1[c]);
+                        if (fs) v = __shfl_down_sync(0xffffffffu, v, fs);
+                        r[c] = fs ? r[c] + v : v;
+                    }
+                }
+            }
             TcFenceBefore();
             __syncwarp();
             if (lane == 0) MbarArrive(&tmem_empty[acc]);  // the accumulator is in registers: release it before the stores
@@ -526,10 +543,10 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
                     if (q * 4 < p.Cout) {
                         const float4 s4 = LdsF4(sc_addr + q * 16), b4 = LdsF4(bi_addr + q * 16);
                         float4 v;
-                        v.x = fmaf(__uint_as_float(r[4 * q]) + __uint_as_float(r1[4 * q]), s4.x, b4.x);
-                        v.y = fmaf(__uint_as_float(r[4 * q + 1]) + __uint_as_float(r1[4 * q + 1]), s4.y, b4.y);
-                        v.z = fmaf(__uint_as_float(r[4 * q + 2]) + __uint_as_float(r1[4 * q + 2]), s4.z, b4.z);
-                        v.w = fmaf(__uint_as_float(r[4 * q + 3]) + __uint_as_float(r1[4 * q + 3]), s4.w, b4.w);
+                        v.x = fmaf(r[4 * q], s4.x, b4.x);
+                        v.y = fmaf(r[4 * q + 1], s4.y, b4.y);
+                        v.z = fmaf(r[4 * q + 2], s4.z, b4.z);
+                        v.w = fmaf(r[4 * q + 3], s4.w, b4.w);
                         if (p.post_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                         *reinterpret_cast<float4*>(orow + q * 4) = v;
                     }
@@ -563,24 +580,31 @@ bool ConvF32x3Supported(const ConvArgs& a) {
 }
 
 int F32x3TileN(const ConvArgs& a) {
-    if (Is3x3(a)) return 64;  // [w0 ; w1] stacked along N
+    if (Is3x3(a)) return kF3WRows;  // [w0 ; w1] x three taps stacked along N
     return a.Cout % 128 == 0 ? 128 : a.Cout % 64 == 0 ? 64 : 32;
 }
-bool F32x3StackedN(const ConvArgs& a) { return Is3x3(a); }
+int F32x3PackedRows(const ConvArgs& a) {
+    if (Is3x3(a)) return kF3WRows;
+    const int bn = F32x3TileN(a);
+    return (a.Cout + bn - 1) / bn * bn;
+}
 int F32x3PackedK(const ConvArgs& a) {
-    if (Is3x3(a)) return 9 * ((a.Cin / 32 + 1) / 2) * 64;
+    if (Is3x3(a)) return 3 * ((a.Cin / 32 + 1) / 2) * 64;
     return a.R * a.S * a.Cin * 2;
 }
 
-// bf16 element index of input channel c of filter tap `tap` inside a packed weight row.  1x1: the residual term sits 32
-// elements further in the same row.  3x3 (stacked N): the residual term sits in row Cout + 32 at the same index; one 128-byte
-// row piece holds two 32-channel planes of one tap.
-int F32x3WeightIndex(const ConvArgs& a, int tap, int c) {
+// (row, bf16 column) of split term `term` (0: w0 = bf16(w), 1: w1 = bf16(w - w0)) of weight (output o, filter tap, input c).
+// 1x1: row o, the two terms 32 columns apart inside the 64-column group of the channel's 32-channel chunk.
+// 3x3: row term*96 + fs*32 + o, column group (filter row, plane pair), 32 columns per plane of the pair.
+void F32x3WeightPos(const ConvArgs& a, int o, int tap, int c, int term, int* row, int* col) {
     if (Is3x3(a)) {
-        const int plane = c / 32, npairs = (a.Cin / 32 + 1) / 2;
-        return (tap * npairs + plane / 2) * 64 + (plane & 1) * 32 + (c % 32);
+        const int plane = c / 32, npairs = (a.Cin / 32 + 1) / 2, fr = tap / 3, fs = tap % 3;
+        *row = term * 96 + fs * 32 + o;
+        *col = (fr * npairs + plane / 2) * 64 + (plane & 1) * 32 + (c % 32);
+        return;
     }
-    return (tap * (a.Cin / 32) + c / 32) * 64 + (c % 32);
+    *row = o;
+    *col = (tap * (a.Cin / 32) + c / 32) * 64 + term * 32 + (c % 32);
 }
 
 cudaError_t ConvF32x3(const ConvArgs& a, const UmmaWeights& w, cudaStream_t stream) {
