@@ -407,10 +407,8 @@ void Replica::BuildDenseRuns() {
     const Plan& P = *plan_;
     if (P.precision != Precision::FP8) return;
     if (const char* e = getenv("B200_ENGINE_DENSEFUSE")) if (e[0] == '0') return;
-    // Fused dense layers over 14x14 tiles for the 56x56 / 28x28 blocks (kernels_dense_tile.cu): correct, but measured SLOWER
-    // than the conv1x1 + conv3x3 kernel pair on B200 (block 1: 941 us against 735 us), so it is opt-in.
-    bool tile_fuse = false;
-    if (const char* e = getenv("B200_ENGINE_TILEFUSE")) tile_fuse = e[0] == '1';
+    // (A fused dense-layer kernel over 14x14 tiles for the 56x56 / 28x28 blocks existed in round 1: bit-identical but slower than
+    // the conv1x1 + conv3x3 pair - block 1: 941 us against 735 us - and was removed; DESIGN.md section 10 keeps the analysis.)
     auto readers = [&](int tensor) {
         int c = 0;
         for (const Step& s : P.steps) c += (s.in == tensor) + (s.in2 == tensor);
@@ -435,8 +433,7 @@ void Replica::BuildDenseRuns() {
         if (ain.buffer != bout.buffer || ain.pitch != bout.pitch || ain.c_off != 0 || bout.c_off != a.Cin) return false;
         if (ain.H != bout.H || ain.W != bout.W || ain.pitch % 16 != 0) return false;
         int ipc = 0, mt = 0;
-        return kernels::DenseBlockGeometry(ain.H, ain.W, &ipc, &mt) ||
-               (tile_fuse && kernels::DenseTileGeometry(ain.H, ain.W) && a.Cin <= kernels::DenseTileMaxCin());
+        return kernels::DenseBlockGeometry(ain.H, ain.W, &ipc, &mt);
     };
     for (size_t i = 0; i < P.steps.size();) {
         if (!pair_ok(i)) { ++i; continue; }
@@ -485,8 +482,6 @@ void Replica::BuildDenseRuns() {
         run.args.buf = BufferPtr(first_in.buffer);
         run.args.pitch = first_in.pitch;
         run.args.H = first_in.H; run.args.W = first_in.W;
-        int ipc = 0, mt = 0;
-        run.tiled = !kernels::DenseBlockGeometry(first_in.H, first_in.W, &ipc, &mt);
         prepared_[i].fused_run = (int)dense_runs_.size();
         dense_runs_.push_back(run);
         i = j;
@@ -613,11 +608,7 @@ size_t Replica::EnqueueAt(size_t i, int n, int off, unsigned u8_mask) {
     kernels::DenseBlockArgs a = run.args;
     a.n = n;
     cudaError_t e = cudaSuccess;
-    if (run.tiled) {
-        for (int l = 0; l < run.num_layers && e == cudaSuccess; ++l) e = kernels::DenseTileFp8(a, l, stream_);
-    } else {
-        e = kernels::DenseBlockFp8(a, stream_);
-    }
+    e = kernels::DenseBlockFp8(a, stream_);
     if (e != cudaSuccess) CudaCheck(e, ("dense block starting at step '" + plan_->steps[i].name + "'").c_str());
     return (size_t)run.num_layers * 2;
 }

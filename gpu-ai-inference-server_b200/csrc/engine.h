@@ -122,7 +122,6 @@ private:
     struct DenseRun {
         size_t first_step = 0;
         int num_layers = 0;
-        bool tiled = false;  // large images: one fused-layer launch per layer over 14x14 tiles (kernels_dense_tile.cu)
         kernels::DenseBlockArgs args;
     };
 

@@ -115,12 +115,6 @@ struct DenseBlockArgs {
 };
 bool DenseBlockGeometry(int H, int W, int* images_per_cta, int* m_tiles);
 cudaError_t DenseBlockFp8(const DenseBlockArgs& a, cudaStream_t stream);
-// ---- ONE dense layer (conv1x1 + conv3x3 fused, bottleneck tensor in shared memory) over 14x14 tiles of larger images
-// (kernels_dense_tile.cu; e4m3, H = W = multiple of 14 above 14).  One launch per layer of the run.
-bool DenseTileGeometry(int H, int W);
-int DenseTileMaxCin();  // conv1 weights are shared-memory resident
-cudaError_t DenseTileFp8(const DenseBlockArgs& a, int layer, cudaStream_t stream);
-
 // ---- memory-bound kernels (templated on element type inside) ----
 cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);
 // uint8 ingestion: raw [n][H][W][C] uint8 pixels -> value / 255 in the internal NHWC layout

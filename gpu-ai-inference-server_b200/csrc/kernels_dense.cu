@@ -14,6 +14,8 @@
 //   epi 1    TMEM -> scale/bias(BN2)+ReLU -> e4m3 -> written straight into a zero-ringed, 128-byte-swizzled patch
 //            in SHARED memory ([slot = padded pixel][128 channels]); the bottleneck tensor never leaves the SM.
 //   phase B  3x3 conv: nine row-shifted UMMA views of the patch x the TMA-loaded 3x3 weights -> 2 x 32 TMEM columns.
+//            14x14 images (padded row = 16 slots): the three taps of a filter row are stacked along N instead (N = 96, three
+//            row-shifted views, see kernels_conv3x3.cu) and epilogue 2 adds the column groups across neighbouring lanes.
 //   epi 2    TMEM -> per-channel scale -> e4m3 -> 32-byte stores into the block buffer's channel slice.
 // Phase A of layer l+1 (all K chunks but the last) overlaps phase B / epi 2 of layer l.
 //
@@ -42,7 +44,8 @@ template <int MT1> struct DbCfg {
     static constexpr int kStages = MT1 == 2 ? 3 : 4;
     static constexpr int kVecBytes = 2 * (128 + 128 + 32 + 32) * 4;          // s1, b1, s2, b2, double buffered
     static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kDbW2Bytes + kDbPatchBytes + kVecBytes + 512;
-    static constexpr int kTmemCols = MT1 == 2 ? 512 : 256;                   // MT1*128 (conv1) + 2*32 (conv2), power of two
+    static constexpr int kTmemCols = MT1 == 2 ? 512 : 256;                   // MT1*128 (conv1) + 2 conv2 accumulators, power of two
+    static constexpr int kAcc2Stride = MT1 == 2 ? 128 : 32;                  // 96 columns used when the taps are stacked
 };
 
 struct DbParams {
@@ -148,6 +151,9 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
     TcFenceAfter();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc1_col = 0, acc2_col = MT1 * 128;
+    // filter-row taps stacked along N: needs the padded row to be exactly 16 slots so that a pixel's left/right neighbours
+    // sit in the same warp's TMEM lanes
+    const bool stack_taps = MT1 == 2 && p.W == 14;
     GridDepLaunch();
 
     if (wrole == 0) {
@@ -246,14 +252,28 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                     MbarWaitWarp(&acc2_empty[t], (k & 1u) ^ 1u);
                     TcFenceAfter();
                     if (ElectOne()) {
+                        const uint32_t d2 = tmem_u + acc2_col + t * Cfg::kAcc2Stride;
+                        if (stack_taps) {
+                            constexpr uint32_t idesc96 = MakeInstrDesc(ME::kFmt, 96);
 #pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int shift = (tap / 3 - 1) * (p.W + 2) + (tap % 3 - 1);
-                            const uint64_t a_desc = MakeSmemDesc(patch_addr + (uint32_t)((t * 128 + shift) * 128));
-                            const uint64_t b_desc = w2_desc + (uint64_t)(tap * (32 * 128 / 16));
+                            for (int fr = 0; fr < 3; ++fr) {
+                                // D[m][fs*32 + o] = A[m + (fr-1)*PW] . W(fr, fs)[o]: the contribution to output slot m - (fs - 1)
+                                const uint64_t a_desc = MakeSmemDesc(patch_addr + (uint32_t)((t * 128 + (fr - 1) * (p.W + 2)) * 128));
+                                const uint64_t b_desc = w2_desc + (uint64_t)(fr * 3 * (32 * 128 / 16));
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks)
-                                UmmaSS<ME::kKind>(tmem_u + acc2_col + t * 32, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc2, (tap | ks) ? 1u : 0u);
+                                for (int ks = 0; ks < 4; ++ks)
+                                    UmmaSS<ME::kKind>(d2, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc96, (fr | ks) ? 1u : 0u);
+                            }
+                        } else {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int shift = (tap / 3 - 1) * (p.W + 2) + (tap % 3 - 1);
+                                const uint64_t a_desc = MakeSmemDesc(patch_addr + (uint32_t)((t * 128 + shift) * 128));
+                                const uint64_t b_desc = w2_desc + (uint64_t)(tap * (32 * 128 / 16));
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    UmmaSS<ME::kKind>(d2, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc2, (tap | ks) ? 1u : 0u);
+                            }
                         }
                         UmmaCommit(&acc2_full[t]);
                         if (t == 1) UmmaCommit(w2_empty);
@@ -397,8 +417,24 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                     TcFenceAfter();
                     if (q == 2) Stamp(p, k, 10 + t);
                     uint32_t r[32];
-                    TmemLoad32(tmem_base + ((uint32_t)(q * 32) << 16) + acc2_col + t * 32, r);
-                    TmemLoadWait();
+                    const uint32_t t2 = tmem_base + ((uint32_t)(q * 32) << 16) + acc2_col + t * Cfg::kAcc2Stride;
+                    if (stack_taps) {
+                        uint32_t r0[32], r2[32];
+                        TmemLoad32(t2, r0);
+                        TmemLoad32(t2 + 32, r);
+                        TmemLoad32(t2 + 64, r2);
+                        TmemLoadWait();
+                        // out[m] = D[m - 1][fs = 0] + D[m][fs = 1] + D[m + 1][fs = 2]; a padded row is 16 lanes, stored pixels are x = 1..14
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const float a0 = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[c]), 1);
+                            const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 1);
+                            r[c] = __float_as_uint((a0 + __uint_as_float(r[c])) + a2);
+                        }
+                    } else {
+                        TmemLoad32(t2, r);
+                        TmemLoadWait();
+                    }
                     TcFenceBefore();
                     __syncwarp();
                     if (lane == 0) MbarArrive(&acc2_empty[t]);

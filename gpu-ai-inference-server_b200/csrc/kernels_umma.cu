@@ -904,13 +904,14 @@ cudaError_t ConvUmma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t strea
         if (ot == DType::BF16) return LaunchBN<__nv_bfloat16, __nv_bfloat16, kModeStem>(bn, tm, p, stream);
         return LaunchBN<__nv_bfloat16, __nv_fp8_e4m3, kModeStem>(bn, tm, p, stream);
     }
-    static const bool l1tma_enabled = [] { const char* e = getenv("B200_ENGINE_L1TMA"); return !(e && e[0] == '0'); }();
+    auto env_on = [](const char* name) { const char* e = getenv(name); return !(e && e[0] == '0'); };  // read per launch: tests toggle them
+    const bool l1tma_enabled = env_on("B200_ENGINE_L1TMA");
     if (l1tma_enabled && Conv1x1TmaSupported(a)) return Conv1x1Tma(a, w, stream);
     // 3x3/s1/p1 bottleneck conv: TMA-loaded swizzled patch, nine row-shifted descriptors (kernels_conv3x3.cu)
-    static const bool c3tma_enabled = [] { const char* e = getenv("B200_ENGINE_C3TMA"); return !(e && e[0] == '0'); }();
+    const bool c3tma_enabled = env_on("B200_ENGINE_C3TMA");
     if (c3tma_enabled && Conv3x3TmaSupported(a)) return Conv3x3Tma(a, w, stream);
     // 3x3/s1/p1 with a narrow output: stage the input patch once in shared memory (9 shifted views)
-    static const bool halo_enabled = [] { const char* e = getenv("B200_ENGINE_HALO"); return !(e && e[0] == '0'); }();
+    const bool halo_enabled = env_on("B200_ENGINE_HALO");
     const int step_k = it == DType::BF16 ? 16 : 32;
     if (halo_enabled && a.R == 3 && a.S == 3 && a.stride == 1 && a.pad == 1 && !a.pre_scale && !a.pool2 && a.Cout <= 32 &&
         a.Cin <= 128 && a.Cin % step_k == 0 && it == ot && a.in.W >= 7) {

@@ -16,8 +16,9 @@
  *   env B200_ENGINE_STAGE_PAGEABLE  = 0 disables the pinned staging of pageable request buffers; B200_ENGINE_STAGING_MB caps the pool (2048);
  *   env B200_ENGINE_CHAIN / B200_ENGINE_CHAIN_MIN_BATCH = device-side serialisation of big forwards across instances (default on, 64);
  *   env B200_ENGINE_PIPELINE_CHUNK  = sub-batch of the H2D/forward pipeline of a lone request (default 128, 0 = off).
- * Kernel selection (debug / A-B measurements): B200_ENGINE_GRAPHS=0, B200_ENGINE_DENSEFUSE=0, B200_ENGINE_TILEFUSE=1 (opt-in fused
- *   dense-layer tile kernel), B200_ENGINE_SPLIT_TRANSITION=0, B200_ENGINE_RESB=0.
+ * Kernel selection (debug / A-B measurements): B200_ENGINE_GRAPHS=0, B200_ENGINE_DENSEFUSE=0, B200_ENGINE_SPLIT_TRANSITION=0,
+ *   B200_ENGINE_RESB=0, B200_ENGINE_L1TMA=0 / B200_ENGINE_C3TMA=0 / B200_ENGINE_HALO=0 (force the generic gather kernels),
+ *   B200_ENGINE_FP32_EXACT=1 (FP32 mode on the exact FFMA kernels instead of tcgen05 with bf16-split operands).
  */
 #ifndef B200_ENGINE_H
 #define B200_ENGINE_H
