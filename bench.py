@@ -540,6 +540,29 @@ def main():
                 mgr2.shutdown()
         except Exception as e:  # noqa: BLE001
             strong = {"error": repr(e)[:300]}
+    # ---------------- BASELINE configs[4]: mixed batch sizes 1..128 from concurrent request threads through ModelInfer ----------------
+    # tools/rest_replay.cpp is the stand-in for the Go REST handler (one OS thread per in-flight request, C-ABI only); it runs
+    # as its own process over every GPU of the job, pinned fp32 request buffers and raw uint8 pixels.
+    replay = None
+    if rank == 0 and not args.no_legs:
+        exe = os.path.join(ROOT, "build", "rest_replay")
+        if os.path.exists(exe):
+            replay = {}
+            env = dict(os.environ, B200_ENGINE_PRECISION=args.precision, B200_ENGINE_MAX_BATCH=str(max(128, B)),
+                       B200_ENGINE_DEVICES=",".join(str(i) for i in range(args.gpus)) if args.gpus > 1 else str(local))
+            env.pop("B200_ENGINE_MIN_SHARD", None)
+            nthreads = str(min(64, 24 + 8 * args.gpus))
+            for key, extra in (("pinned_fp32", ["--pinned"]), ("pinned_uint8", ["--pinned", "--uint8"])):
+                try:
+                    r = subprocess.run([exe, "--repo", os.path.join(ROOT, "models"), "--threads", nthreads, "--requests", str(1500 * args.gpus)] + extra,
+                                       capture_output=True, text=True, timeout=300, env=env)
+                    ln = [x for x in r.stdout.splitlines() if x.startswith("{")]
+                    j = json.loads(ln[-1])
+                    replay[key] = {k: j[k] for k in ("images_per_s", "requests_per_s", "latency_ms_p50", "latency_ms_p99", "threads", "requests", "failed", "gpus_visible")}
+                except Exception as e:  # noqa: BLE001
+                    replay[key] = {"error": repr(e)[:200]}
+            replay["note"] = "closed loop, batch sizes drawn uniformly from {1,2,4,...,128}; tools/rest_replay.cpp (BASELINE.json configs[4])"
+
     if rank == 0:
         peaks = _peaks()
         box = {} if args.no_legs else measure_box_peaks(local)
@@ -613,7 +636,7 @@ def main():
                               "api": "ModelInfer with DATATYPE_UINT8 [N,H,W,3] pixels (extension; value/255 + layout on the GPU)",
                               "logits_identical_to_float_path": u8_equal},
                 "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_1thread": cpu1, "latency": lat, "legs": legs,
-                "strong_scaling": strong, "box_peaks": box,
+                "strong_scaling": strong, "mixed_replay": replay, "box_peaks": box,
                 "wall_clock_check_ms_per_step": 1e3 * t_wall / args.steps}
     if line is not None:
         print(json.dumps(line))

@@ -352,8 +352,9 @@ cudaError_t LaunchFsL1(const CUtensorMap& tw, const CUtensorMap& tin, const CUte
 // i.e. 2 A fetches per (filter row, K step) instead of 9 x 3 = 27 single products.  The epilogue computes
 //     out[m][o] = sum over fs of ( D[m + fs][fs*32 + o] + D[m + fs][96 + fs*32 + o] )       (warp shuffles across TMEM lanes)
 // A weight tile row is 128 B = two planes of one tap ([plane 2p | plane 2p+1]).
-constexpr int kF3Threads = 32 * 14;   // 8 transform + 4 epilogue + TMA + MMA
-constexpr int kF3XfWarps = 8;
+constexpr int kF3Threads = 32 * 16;   // 10 transform + 4 epilogue + TMA + MMA
+constexpr int kF3XfWarps = 10;        // one warp per patch row (TH + 2 <= 10): a plane is split in ONE pass (two passes of 8 warps
+                                      // made the transform, not the MMAs, the slowest stage: ~1200 against 912 cycles per plane)
 constexpr int kF3PW = 16;
 constexpr int kF3PatchBytes = 10 * kF3PW * 128;
 constexpr int kF3WRows = 192;
@@ -394,7 +395,7 @@ conv3x3_f32x3_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kNW = kF3Threads / 32;
-    const int wrole = warp >= kNW - 2 ? warp - (kNW - 2) : warp + 2;  // 0 TMA, 1 MMA, 2..9 transform, 10..13 epilogue
+    const int wrole = warp >= kNW - 2 ? warp - (kNW - 2) : warp + 2;  // 0 TMA, 1 MMA, 2..11 transform, 12..15 epilogue
     const int npairs = (p.planes + 1) >> 1;
 
     if (wrole == 0 && lane == 0) {
