@@ -529,7 +529,16 @@ def main():
                         return time.perf_counter() - t0
                     run([3] * clients)
                     return B * e2e_steps / run(todo)
-                strong = {"n_gpus": args.gpus, "global_batch": B, "shard_per_gpu": per, "scheduler": "ModelImpl::Execute (persistent per-GPU workers)",
+                h2d = {}
+                try:
+                    for wc in (False, True):
+                        one, allg = pkg.measure_h2d(args.gpus, 256, 8, wc)
+                        h2d["write_combined" if wc else "pinned"] = {"one_gpu_gbs": one, "all_gpus_gbs": allg}
+                    h2d["note"] = ("host->device copy ceiling of this box (B200MeasureH2D: 256 MB x 8 per GPU, GPU 0 alone, then all GPUs at once): "
+                                   "e2e with fp32 input needs 0.602 MB per image")
+                except Exception as e:  # noqa: BLE001
+                    h2d = {"error": repr(e)[:200]}
+                strong = {"n_gpus": args.gpus, "global_batch": B, "host_to_device": h2d, "shard_per_gpu": per, "scheduler": "ModelImpl::Execute (persistent per-GPU workers)",
                           "device_value": B * args.steps / (float(sms.sum()) * 1e-3), "device_ms_per_step": float(sms.mean()),
                           "e2e_fp32": leg(mk_f32, E2E_CLIENTS), "e2e_fp32_serial": leg(mk_f32, 1),
                           "e2e_uint8": leg(mk_u8, E2E_CLIENTS), "e2e_uint8_serial": leg(mk_u8, 1), "unit": UNIT,

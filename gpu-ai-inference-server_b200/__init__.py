@@ -12,5 +12,5 @@ from .binding import (  # noqa: F401
     DataType, DeviceType, ModelType, TensorData, OutputConfig, ModelConfig, ModelMetadata, ModelStats,
     MemoryInfo, InferenceManager, Model, EngineError,
     is_cuda_available, get_device_count, get_device_info, get_memory_info,
-    library_path, load_library, plan_describe, plan_shards, kernel_launch_count, engine_version,
+    library_path, load_library, plan_describe, plan_shards, kernel_launch_count, engine_version, measure_h2d,
 )

@@ -106,8 +106,16 @@ EXPORTED_SYMBOLS = [
 ]
 EXTENSION_SYMBOLS = [
     "B200EngineVersion", "B200PlanDescribe", "B200PlanShards", "B200KernelLaunchCount", "B200ModelStageInput", "B200ModelForwardDevice",
-    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats", "B200HostAlloc", "B200HostFree", "B200ModelInferTopK", "B200ModelFaultedReplicas",
+    "B200ModelReadOutput", "B200ModelProfileSteps", "B200ModelReadValue", "B200ModelCoalesceStats", "B200HostAlloc", "B200HostFree", "B200ModelInferTopK", "B200ModelFaultedReplicas", "B200MeasureH2D",
 ]
+
+
+def measure_h2d(gpus: int, mbytes: int = 256, iters: int = 8, write_combined: bool = False):
+    """(GB/s to GPU 0 alone, aggregate GB/s to `gpus` GPUs at once) from page-locked host memory (B200MeasureH2D)."""
+    one, allg, e = C.c_double(0), C.c_double(0), C.c_void_p()
+    if not load_library().B200MeasureH2D(int(gpus), int(mbytes) << 20, int(iters), 1 if write_combined else 0, C.byref(one), C.byref(allg), C.byref(e)):
+        raise EngineError(_take_error(e, "H2D measurement failed"))
+    return float(one.value), float(allg.value)
 
 
 def library_path() -> str:
@@ -150,6 +158,7 @@ def load_library() -> C.CDLL:
         "B200ModelCoalesceStats": (b, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
         "B200HostAlloc": (vp, [sz]), "B200HostFree": (None, [vp]),
         "B200ModelFaultedReplicas": (i, [vp]),
+        "B200MeasureH2D": (b, [i, sz, i, i, C.POINTER(C.c_double), C.POINTER(C.c_double), err]),
         "B200ModelInferTopK": (b, [vp, C.POINTER(CTensorData), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(vp)]),
     }
     for name, (res, args) in sig.items():

@@ -2,11 +2,14 @@
 // inspection, parity debugging).  Not part of the reference ABI.
 #include "b200_engine.h"
 
+#include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <future>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "engine.h"
 #include "kernels.h"
@@ -45,6 +48,60 @@ void* B200HostAlloc(size_t bytes) {
 }
 void B200HostFree(void* ptr) {
     if (ptr) cudaFreeHost(ptr);
+}
+
+bool B200MeasureH2D(int gpus, size_t bytes, int iters, int write_combined, double* gbs_single, double* gbs_all, ErrorMessage* error) {
+    try {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) throw std::runtime_error("no CUDA device");
+        gpus = std::max(1, std::min(gpus, ndev));
+        iters = std::max(1, iters);
+        if (bytes < (1u << 20) || !gbs_single || !gbs_all) throw std::runtime_error("Invalid parameters");
+        struct Lane { void* host = nullptr; void* dev = nullptr; cudaStream_t stream = nullptr; };
+        std::vector<Lane> lanes((size_t)gpus);
+        auto cleanup = [&] {
+            for (int g = 0; g < gpus; ++g) {
+                cudaSetDevice(g);
+                if (lanes[g].stream) cudaStreamDestroy(lanes[g].stream);
+                if (lanes[g].dev) cudaFree(lanes[g].dev);
+                if (lanes[g].host) cudaFreeHost(lanes[g].host);
+            }
+        };
+        try {
+            for (int g = 0; g < gpus; ++g) {
+                b200::CudaCheck(cudaSetDevice(g), "cudaSetDevice");
+                b200::CudaCheck(cudaHostAlloc(&lanes[g].host, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)), "cudaHostAlloc");
+                memset(lanes[g].host, 1, bytes);
+                b200::CudaCheck(cudaMalloc(&lanes[g].dev, bytes), "cudaMalloc");
+                b200::CudaCheck(cudaStreamCreateWithFlags(&lanes[g].stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            }
+            auto run = [&](int g) {
+                cudaSetDevice(g);
+                for (int i = 0; i < iters; ++i) cudaMemcpyAsync(lanes[g].dev, lanes[g].host, bytes, cudaMemcpyHostToDevice, lanes[g].stream);
+                b200::CudaCheck(cudaStreamSynchronize(lanes[g].stream), "H2D");
+            };
+            run(0);  // warm-up
+            auto t0 = std::chrono::steady_clock::now();
+            run(0);
+            double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            *gbs_single = (double)bytes * iters / dt / 1e9;
+            std::vector<std::future<void>> f;
+            t0 = std::chrono::steady_clock::now();
+            for (int g = 1; g < gpus; ++g) f.push_back(std::async(std::launch::async, run, g));
+            run(0);
+            for (auto& x : f) x.get();
+            dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            *gbs_all = (double)bytes * iters * gpus / dt / 1e9;
+        } catch (...) {
+            cleanup();
+            throw;
+        }
+        cleanup();
+        return true;
+    } catch (const std::exception& e) {
+        SetErr(error, e.what());
+        return false;
+    }
 }
 
 const char* B200EngineVersion(void) { return "b200-engine 0.1 sm_100a"; }

@@ -86,6 +86,11 @@ bool B200ModelInferTopK(ModelHandle handle, const TensorData* inputs, int num_in
 void* B200HostAlloc(size_t bytes);
 void B200HostFree(void* ptr);
 
+/* Host->device copy bandwidth of this box, the ceiling of every end-to-end figure: `bytes` per GPU are copied `iters` times from
+ * page-locked host memory (write-combined when `write_combined` != 0) to each of the first `gpus` devices, first on GPU 0 alone
+ * (*gbs_single), then on all of them at once from one host thread per GPU (*gbs_all, aggregate).  GB/s = 1e9 bytes/s. */
+bool B200MeasureH2D(int gpus, size_t bytes, int iters, int write_combined, double* gbs_single, double* gbs_all, ErrorMessage* error);
+
 #ifdef __cplusplus
 }
 #endif
