@@ -23,7 +23,7 @@ LIB = os.path.join(PKG, "lib", "libinference_engine.so")
 
 SOURCES = [
     "onnx_wire.cpp", "plan.cpp", "model_repository.cpp", "inference_manager.cpp", "model.cpp",
-    "inference_bridge.cpp", "b200_api.cpp", "engine.cu", "cuda_utils.cu", "kernels_simt.cu", "kernels_umma.cu", "kernels_stem.cu", "kernels_conv3x3.cu", "kernels_conv1x1.cu", "kernels_dense.cu", "kernels_poolbn.cu", "kernels_f32x3.cu", "tmap.cu",
+    "inference_bridge.cpp", "b200_api.cpp", "engine.cu", "cuda_utils.cu", "kernels_simt.cu", "kernels_umma.cu", "kernels_stem.cu", "kernels_conv3x3.cu", "kernels_conv1x1.cu", "kernels_dense.cu", "kernels_dense_stream.cu", "kernels_poolbn.cu", "kernels_f32x3.cu", "tmap.cu",
 ]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -150,9 +150,12 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
     if (const char* pc = getenv("B200_ENGINE_CHAIN_MIN_BATCH")) chain_min_batch_ = atoi(pc);
     CudaCheck(cudaEventCreate(&ev0_), "cudaEventCreate");
     CudaCheck(cudaEventCreate(&ev1_), "cudaEventCreate");
-    CudaCheck(cudaMalloc((void**)&arena_, plan_->arena_bytes + 4096), "cudaMalloc(arena)");
-    CudaCheck(cudaMemsetAsync(arena_, 0, plan_->arena_bytes + 4096, stream_), "cudaMemset(arena)");
-    device_bytes_ += plan_->arena_bytes + 4096;
+    // a guard in front of the first buffer: the streaming dense-layer kernel's TMA boxes begin one pixel before a row
+    constexpr size_t kArenaGuard = 4096;
+    CudaCheck(cudaMalloc((void**)&arena_alloc_, plan_->arena_bytes + 4096 + kArenaGuard), "cudaMalloc(arena)");
+    CudaCheck(cudaMemsetAsync(arena_alloc_, 0, plan_->arena_bytes + 4096 + kArenaGuard, stream_), "cudaMemset(arena)");
+    arena_ = arena_alloc_ + kArenaGuard;
+    device_bytes_ += plan_->arena_bytes + 4096 + kArenaGuard;
 
     const Plan& P = *plan_;
     // fp32 device copies of per-channel vectors, uploaded lazily below
@@ -220,6 +223,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
             const Prepared& lp = weights_of_->prepared_[i];
             pr.w_kn = lp.w_kn;
             pr.umma = lp.umma;
+            pr.h_out_scale = lp.h_out_scale;
             continue;
         }
         if (pr.use_f32x3) {
@@ -321,6 +325,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
                     }
         pr.umma.w = Upload(packed.data(), packed.size());
         pr.umma.out_scale = (const float*)Upload(scale.data(), scale.size() * 4);
+        pr.h_out_scale = scale;
         pr.umma.K_pad = K_pad;
         pr.umma.Cout_pad = cout_pad;
         // TMA descriptor over the packed weights: dims {K_pad, Cout_pad}, box {kc, bn}, 128-byte swizzle
@@ -341,6 +346,7 @@ Replica::Replica(int device, std::shared_ptr<const Plan> plan, bool use_graphs, 
     }
     if (weights_of_) BorrowDenseRuns(*weights_of_);
     else BuildDenseRuns();
+    MarkStreamPairs();
     // fp32 reference mode: scratch for the deterministic split-K of the SIMT convolutions at small batch
     {
         bool any_simt = false;
@@ -488,6 +494,46 @@ void Replica::BuildDenseRuns() {
     }
 }
 
+// Dense layers of the large-image blocks (56x56, 28x28; e4m3): the (1x1 conv, 3x3 conv) step pair can run as ONE streaming kernel
+// that keeps the 128-channel bottleneck in shared memory (kernels_dense_stream.cu).  Bit-identical to the kernel pair and half the
+// HBM traffic, but measured SLOWER at bs256 (2.20 ms against 2.00 ms per forward; both are bound by the per-instruction cost of
+// small-N tcgen05.mma and by the tcgen05.ld rate), so it is opt-in: B200_ENGINE_LAYERFUSE=1.
+void Replica::MarkStreamPairs() {
+    const Plan& P = *plan_;
+    if (P.precision != Precision::FP8) return;
+    const char* lf = getenv("B200_ENGINE_LAYERFUSE");
+    if (!(lf && lf[0] == '1')) return;
+    auto readers = [&](int tensor) {
+        int c = 0;
+        for (const Step& s : P.steps) c += (s.in == tensor) + (s.in2 == tensor);
+        for (int o : P.outputs) c += (o == tensor);
+        return c;
+    };
+    for (size_t i = 0; i + 1 < P.steps.size(); ++i) {
+        const Step& a = P.steps[i];
+        const Step& b = P.steps[i + 1];
+        Prepared& pa = prepared_[i];
+        const Prepared& pb = prepared_[i + 1];
+        if (pa.fused_run >= 0 || a.kind != StepKind::Conv || b.kind != StepKind::Conv) continue;
+        if (!pa.use_umma || !pb.use_umma || !pa.umma.tensor_map || !pb.umma.tensor_map) continue;
+        if (a.R != 1 || a.S != 1 || a.stride != 1 || a.pad != 0 || a.pool2_fused || a.stem_nchw || a.pre_scale < 0 || a.pre_shift < 0) continue;
+        if (b.R != 3 || b.S != 3 || b.stride != 1 || b.pad != 1 || b.pool2_fused || b.pre_scale >= 0) continue;
+        if (a.Cout != 128 || b.Cin != 128 || b.Cout != 32) continue;
+        if (b.in != a.out || readers(a.out) != 1) continue;
+        const TensorDesc& ain = P.tensors[a.in];
+        const TensorDesc& bout = P.tensors[b.out];
+        if (ain.dtype != DType::FP8 || bout.dtype != DType::FP8 || P.tensors[a.out].dtype != DType::FP8) continue;
+        if (ain.buffer != bout.buffer || ain.pitch != bout.pitch || ain.c_off != 0 || bout.c_off != a.Cin) continue;
+        if (ain.H != bout.H || ain.W != bout.W) continue;
+        if (P.buffers[ain.buffer].role != BufferDesc::Role::Arena) continue;  // graph I/O buffers are indexed by the sub-batch offset
+        if (pa.h_out_scale.size() != 128 || pb.h_out_scale.size() != 32) continue;
+        if ((int)P.consts[a.pre_scale].data.size() < a.Cin || (int)P.consts[a.pre_shift].data.size() < a.Cin) continue;
+        if (!kernels::DenseLayerStreamSupported(ain.H, ain.W, a.Cin, ain.pitch)) continue;
+        pa.stream_pair = true;
+        ++i;  // the 3x3 conv is consumed by the pair
+    }
+}
+
 Replica::~Replica() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
@@ -499,7 +545,7 @@ Replica::~Replica() {
             if (pr.umma.tensor_map) delete (CUtensorMap*)pr.umma.tensor_map;
     for (void* p : allocations_) cudaFree(p);
     if (flush_buf_) cudaFree(flush_buf_);
-    if (arena_) cudaFree(arena_);
+    if (arena_alloc_) cudaFree(arena_alloc_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -600,6 +646,29 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
 
 size_t Replica::EnqueueAt(size_t i, int n, int off, unsigned u8_mask) {
     const int r = prepared_[i].fused_run;
+    if (r < 0 && prepared_[i].stream_pair) {
+        const Plan& P = *plan_;
+        const Step& a = P.steps[i];
+        const Step& b = P.steps[i + 1];
+        const Prepared& pa = prepared_[i];
+        const Prepared& pb = prepared_[i + 1];
+        kernels::DenseLayerStreamArgs d;
+        d.w1_map = pa.umma.tensor_map;
+        d.w2_map = pb.umma.tensor_map;
+        d.buf = pa.in.base;
+        d.pitch = pa.in.pitch; d.n = n; d.H = pa.in.H; d.W = pa.in.W;
+        d.Cin = a.Cin; d.c_off_out = pb.out.c_off;
+        d.pre_relu = a.pre_relu; d.relu1 = a.post_relu; d.relu2 = b.post_relu;
+        d.pre_scale = P.consts[a.pre_scale].data.data();
+        d.pre_shift = P.consts[a.pre_shift].data.data();
+        d.s1 = pa.h_out_scale.data();
+        d.b1 = a.bias >= 0 ? P.consts[a.bias].data.data() : nullptr;
+        d.s2 = pb.h_out_scale.data();
+        d.b2 = b.bias >= 0 ? P.consts[b.bias].data.data() : nullptr;
+        cudaError_t e = kernels::DenseLayerStreamFp8(d, stream_);
+        if (e != cudaSuccess) CudaCheck(e, ("dense layer (streaming) starting at step '" + a.name + "'").c_str());
+        return 2;
+    }
     if (r < 0) {
         EnqueueStep(i, n, off, u8_mask);
         return 1;

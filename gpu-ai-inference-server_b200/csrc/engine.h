@@ -117,6 +117,8 @@ private:
         size_t in_io_stride = 0, in2_io_stride = 0, out_io_stride = 0;  // bytes per sample when the view is graph I/O
         int fused_run = -1;  // index into dense_runs_ when this step starts a run executed by the dense-block kernel
         bool split_pool = false;  // wide transition: pooled BN+ReLU A operand materialised once, then a plain 1x1 conv
+        bool stream_pair = false; // this 1x1 conv and the 3x3 conv after it run as ONE streaming dense-layer kernel (kernels_dense_stream.cu)
+        std::vector<float> h_out_scale;  // host copy of umma.out_scale (kernel-parameter constants of the streaming kernel)
     };
     // Consecutive (1x1 conv, 3x3 conv) step pairs of one dense block executed by ONE persistent kernel.
     struct DenseRun {
@@ -133,6 +135,7 @@ private:
     const uint8_t* U8Source(int tensor, int off, unsigned u8_mask);  // device uint8 staging of a graph input, or null  // runs step i (or the fused run starting there); returns steps consumed
     void BuildDenseRuns();
     void BorrowDenseRuns(const Replica& lender);
+    void MarkStreamPairs();
     kernels::View MakeView(int tensor) const;
     void* BufferPtr(int buffer) const;
     void* Upload(const void* host, size_t bytes);
@@ -149,6 +152,7 @@ private:
     int pipeline_chunk_ = 128;  // sub-batch size of the H2D/compute pipeline (B200_ENGINE_PIPELINE_CHUNK, 0 = off)
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     char* arena_ = nullptr;
+    char* arena_alloc_ = nullptr;  // cudaMalloc'ed block; arena_ starts kArenaGuard bytes into it (TMA boxes that begin one pixel early)
     void* flush_buf_ = nullptr;
     void* splitk_scratch_ = nullptr;  // fp32 SIMT split-K: tile counters + partial sums (small batches)
     size_t splitk_bytes_ = 0;

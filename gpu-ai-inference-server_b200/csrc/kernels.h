@@ -115,6 +115,25 @@ struct DenseBlockArgs {
 };
 bool DenseBlockGeometry(int H, int W, int* images_per_cta, int* m_tiles);
 cudaError_t DenseBlockFp8(const DenseBlockArgs& a, cudaStream_t stream);
+// ---- one dense layer (1x1 -> 128 -> 3x3 -> 32) of the 56x56 / 28x28 blocks as a streaming kernel (kernels_dense_stream.cu; e4m3):
+// the bottleneck tensor stays in shared memory, the conv1 A operand goes through tensor memory.  Per-channel constants are HOST
+// arrays (they travel as kernel parameters).
+struct DenseLayerStreamArgs {
+    const void* w1_map = nullptr;   // host CUtensorMap*: conv1 weights [128][K_pad] e4m3, box {128, 128}
+    const void* w2_map = nullptr;   // host CUtensorMap*: conv2 weights [32][9*128] e4m3, box {128, 32}
+    void* buf = nullptr;            // block buffer (NHWC e4m3); at least one pixel of readable memory in front of it
+    int pitch = 0, n = 0, H = 0, W = 0;
+    int Cin = 0, c_off_out = 0;
+    int pre_relu = 0, relu1 = 0, relu2 = 0;
+    const float* pre_scale = nullptr;  // [Cin] folded BN1 (host)
+    const float* pre_shift = nullptr;
+    const float* s1 = nullptr;         // [128] conv1 epilogue scale / bias (host; bias may be null)
+    const float* b1 = nullptr;
+    const float* s2 = nullptr;         // [32] conv2 epilogue (host)
+    const float* b2 = nullptr;
+};
+bool DenseLayerStreamSupported(int H, int W, int Cin, int pitch);
+cudaError_t DenseLayerStreamFp8(const DenseLayerStreamArgs& a, cudaStream_t stream);
 // ---- memory-bound kernels (templated on element type inside) ----
 cudaError_t NchwToNhwc(const float* in, View out, int n, cudaStream_t stream);
 // uint8 ingestion: raw [n][H][W][C] uint8 pixels -> value / 255 in the internal NHWC layout

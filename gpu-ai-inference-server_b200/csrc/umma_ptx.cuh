@@ -33,8 +33,21 @@ __device__ __forceinline__ void MbarArrive(uint64_t* bar) {
 __device__ __forceinline__ void MbarArriveExpectTx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
 }
+#ifndef B200_TRYWAIT_HINT_NS
+#define B200_TRYWAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if B200_TRYWAIT_HINT_NS > 0
+    // suspend-time hint: the hardware may keep the thread suspended up to this long before try_wait returns false
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(SmemAddr(bar)), "r"(parity), "r"((uint32_t)B200_TRYWAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -42,6 +55,7 @@ __device__ __forceinline__ bool MbarTryWait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(SmemAddr(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Non-blocking probe (mbarrier.test_wait never suspends the thread).
@@ -150,6 +164,11 @@ __device__ __forceinline__ void TmaLoad5D(void* smem_dst, const CUtensorMap* map
 __device__ __forceinline__ void TmaStore2D(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"((uint64_t)map), "r"(SmemAddr(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void TmaStore5D(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"((uint64_t)map), "r"(SmemAddr(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                  : "memory");
 }
 __device__ __forceinline__ void BulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -279,6 +298,33 @@ __device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 __device__ __forceinline__ void TmemLoadWait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void TmemLoad16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane (registers -> tensor memory)
+__device__ __forceinline__ void TmemStore16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void TmemStoreWait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T (kind::f8f6f4): the A tile lives in tensor memory, row = lane, K packed 4 e4m3 per
+// 32-bit column (a 32-byte K step = 8 columns)
+__device__ __forceinline__ void UmmaTS(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
