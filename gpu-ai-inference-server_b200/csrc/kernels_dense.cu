@@ -56,6 +56,7 @@ struct DbParams {
     int n, H, W;
     int ipc;                       // images per CTA pass
     int num_groups;
+    int interleave;                // a CTA that owns two image groups alternates between them layer by layer
     unsigned long long* trace;  // debug: [unit][16] globaltimer stamps of CTA 0 (B200_DENSE_TRACE), else null
 };
 
@@ -89,6 +90,29 @@ __device__ __forceinline__ DbGeom DbGeomOf(int c, int Cin) {
     return g;
 }
 
+// The order of the (image group, layer) units of one CTA, identical for every role.  A unit's last K chunk needs the 32 channels
+// the previous layer of the SAME images appended (global-memory round trip: stores, fences, TMA reload); a CTA that owns two
+// groups therefore alternates between them layer by layer, so that this hand-over hides behind the other group's unit.
+//   f(k, grp, l, slot): k = running unit index of this CTA, slot = 0 / 1 = which of the two interleaved groups
+template <typename F>
+__device__ __forceinline__ void DbWalk(const DbParams& p, F&& f) {
+    uint32_t k = 0;
+    const int stride = (int)gridDim.x;
+    if (p.interleave) {
+        for (int g = blockIdx.x; g < p.num_groups; g += 2 * stride) {
+            const int gb = g + stride;
+            const bool two = gb < p.num_groups;
+            for (int l = 0; l < p.num_layers; ++l) {
+                f(k++, g, l, 0);
+                if (two) f(k++, gb, l, 1);
+            }
+        }
+    } else {
+        for (int g = blockIdx.x; g < p.num_groups; g += stride)
+            for (int l = 0; l < p.num_layers; ++l) f(k++, g, l, 0);
+    }
+}
+
 template <int MT1>
 __global__ void __launch_bounds__(kDbThreads, 1)
 dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p) {
@@ -114,8 +138,8 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
     uint64_t* patch_full = acc1_empty + 1;
     uint64_t* acc2_full = patch_full + 1;   // [2]
     uint64_t* acc2_empty = acc2_full + 2;   // [2]
-    uint64_t* out_ready = acc2_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_ready + 1);
+    uint64_t* out_ready = acc2_empty + 2;   // [2]: one per interleaved group slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_ready + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // the single-thread roles sit on the highest warp ids (the issue arbiter prefers high warp ids; see kernels_conv1x1.cu)
@@ -138,7 +162,8 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
             MbarInit(&acc2_full[t], 1);
             MbarInit(&acc2_empty[t], kDbEpiThreads / 32);
         }
-        MbarInit(out_ready, kDbEpiThreads / 32);
+        MbarInit(&out_ready[0], kDbEpiThreads / 32);
+        MbarInit(&out_ready[1], kDbEpiThreads / 32);
         FenceBarrierInit();
         PrefetchTensorMap(&tmap_x);
     }
@@ -160,41 +185,42 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
         // =========================================================== TMA producer
         GridDepWait();
         int stage = 0;
-        uint32_t phase = 0, k = 0;
-        for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+        uint32_t phase = 0;
+        uint32_t units_of[2] = {0u, 0u};  // units finished per group slot = phases of out_ready[slot]
+        DbWalk(p, [&](uint32_t k, int grp, int l, int slot) {
             const int row0 = grp * p.ipc * HW;
-            for (int l = 0; l < p.num_layers; ++l, ++k) {
-                const DenseLayerDesc* L = p.layers + l;
-                const int Cin = L->Cin;
-                const int nc = (Cin + kDbCH - 1) / kDbCH;
-                for (int c = 0; c < nc; ++c) {
-                    if (c == nc - 1) {
-                        // 3x3 weights of this layer (their buffer is free once phase B of the previous unit has run) ...
-                        MbarWaitWarp(w2_empty, (k & 1u) ^ 1u);
-                        if (ElectOne()) {
-                            MbarArriveExpectTx(w2_full, (uint32_t)kDbW2Bytes);
-                            for (int t = 0; t < 9; ++t) TmaLoad2DGlobalMap(s_w2 + t * 32 * 128, &L->w2, w2_full, t * kDbCH, 0);
-                        }
-                        __syncwarp();
-                        // ... and the last K chunk holds the 32 channels the previous layer has just appended
-                        MbarWaitWarp(out_ready, (k & 1u) ^ 1u);
-                        Stamp(p, k, 1);
-                    }
-                    MbarWaitWarp(&empty_bar[stage], phase ^ 1u);
-                    if (c == nc - 1) Stamp(p, k, 2);
-                    if (ElectOne()) {
-                        const DbGeom g = DbGeomOf(c, Cin);
-                        uint8_t* dst = smem + stage * Cfg::kStageBytes;
-                        MbarArriveExpectTx(&raw_full[stage], (uint32_t)Cfg::kStageBytes);
-#pragma unroll
-                        for (int t = 0; t < MT1; ++t) TmaLoad2D(dst + t * kATileBytes, &tmap_x, &raw_full[stage], g.ch_base, row0 + t * kTileM);
-                        TmaLoad2DGlobalMap(dst + MT1 * kATileBytes, &L->w1, &raw_full[stage], g.ch_base, 0);
-                    }
-                    __syncwarp();
-                    if (++stage == NS) { stage = 0; phase ^= 1u; }
+            const DenseLayerDesc* L = p.layers + l;
+            const int Cin = L->Cin;
+            const int nc = (Cin + kDbCH - 1) / kDbCH;
+            for (int c = 0; c < nc; ++c) {
+                if (c == nc - 1) {
+                    // the last K chunk holds the 32 channels the previous layer of THESE images has just appended
+                    MbarWaitWarp(&out_ready[slot], (units_of[slot] & 1u) ^ 1u);
+                    Stamp(p, k, 1);
                 }
+                MbarWaitWarp(&empty_bar[stage], phase ^ 1u);
+                if (c == nc - 1) Stamp(p, k, 2);
+                if (ElectOne()) {
+                    const DbGeom g = DbGeomOf(c, Cin);
+                    uint8_t* dst = smem + stage * Cfg::kStageBytes;
+                    MbarArriveExpectTx(&raw_full[stage], (uint32_t)Cfg::kStageBytes);
+#pragma unroll
+                    for (int t = 0; t < MT1; ++t) TmaLoad2D(dst + t * kATileBytes, &tmap_x, &raw_full[stage], g.ch_base, row0 + t * kTileM);
+                    TmaLoad2DGlobalMap(dst + MT1 * kATileBytes, &L->w1, &raw_full[stage], g.ch_base, 0);
+                }
+                __syncwarp();
+                if (++stage == NS) { stage = 0; phase ^= 1u; }
             }
-        }
+            // 3x3 weights of this layer, AFTER the last A chunk: their buffer is free only once phase B of the previous unit has
+            // run, and with two interleaved groups that is later than the moment the last chunk can be fetched
+            MbarWaitWarp(w2_empty, (k & 1u) ^ 1u);
+            if (ElectOne()) {
+                MbarArriveExpectTx(w2_full, (uint32_t)kDbW2Bytes);
+                for (int t = 0; t < 9; ++t) TmaLoad2DGlobalMap(s_w2 + t * 32 * 128, &L->w2, w2_full, t * kDbCH, 0);
+            }
+            __syncwarp();
+            ++units_of[slot];
+        });
     } else if (wrole == 1) {
         // =========================================================== MMA issuer
         constexpr uint32_t idesc1 = MakeInstrDesc(ME::kFmt, 128);
@@ -204,9 +230,9 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
         const uint32_t patch_addr = SmemAddr(s_patch) + kDbMargin * 128;
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int stage = 0;
-        uint32_t phase = 0, k = 0;
-        for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
-            for (int l = 0; l < p.num_layers; ++l, ++k) {
+        uint32_t phase = 0;
+        DbWalk(p, [&](uint32_t k, int, int l, int) {
+            {
                 const int Cin = p.layers[l].Cin;
                 const int nc = (Cin + kDbCH - 1) / kDbCH;
                 // ---- phase A: the conv1 accumulators must have been drained by epilogue 1 of the previous unit
@@ -282,7 +308,7 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                 }
                 Stamp(p, k, 7);
             }
-        }
+        });
     } else if (wrole < 2 + kDbXfWarps) {
         // =========================================================== transform warps: in-place BN1 + ReLU on the A tiles
         const int tw = wrole - 2;
@@ -295,8 +321,8 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
         const uint32_t smem_base = SmemAddr(smem);
         int stage = 0;
         uint32_t phase = 0;
-        for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
-            for (int l = 0; l < p.num_layers; ++l) {
+        DbWalk(p, [&](uint32_t k, int, int l, int) {
+            {
                 const DenseLayerDesc* L = p.layers + l;
                 const int Cin = L->Cin;
                 const int nc = (Cin + kDbCH - 1) / kDbCH;
@@ -318,7 +344,7 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                         sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
                     }
                     MbarWaitWarp(&raw_full[stage], phase);
-                    if (c == nc - 1 && tw == 7) Stamp(p, grp == (int)blockIdx.x ? (uint32_t)l : 64u, 3);
+                    if (c == nc - 1 && tw == 7) Stamp(p, k, 3);
                     if (mine) {
 #pragma unroll
                         for (int t = 0; t < MT1; ++t) {
@@ -335,11 +361,11 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                     FenceProxyAsync();
                     __syncwarp();
                     if (lane == 0) MbarArrive(&xf_full[stage]);  // one arrive per warp: 256 per-thread arrives serialise on the barrier word
-                    if (c == nc - 1) Stamp(p, grp == (int)blockIdx.x ? (uint32_t)l : 64u, 4);
+                    if (c == nc - 1) Stamp(p, k, 4);
                     if (++stage == NS) { stage = 0; phase ^= 1u; }
                 }
             }
-        }
+        });
     } else {
         // =========================================================== epilogue warps (TMEM lane quarter = warp & 3)
         const int q = warp & 3;
@@ -365,11 +391,10 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
             pix_rel[t] = (img < p.ipc && yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) ? img * HW + (yy - 1) * p.W + (xx - 1) : -1;
         }
         GridDepWait();
-        uint32_t k = 0;
-        for (int grp = blockIdx.x; grp < p.num_groups; grp += gridDim.x) {
+        DbWalk(p, [&](uint32_t k, int grp, int l, int slot) {
             const int img0 = grp * p.ipc;
             const int n_valid = (p.n - img0 < p.ipc ? p.n - img0 : p.ipc) * HW;  // pixels of this group that exist
-            for (int l = 0; l < p.num_layers; ++l, ++k) {
+            {
                 const DenseLayerDesc* L = p.layers + l;
                 float* vec = s_vec + (k & 1u) * 320;
                 // per-channel vectors of this layer -> shared memory (double buffered by unit parity)
@@ -452,10 +477,10 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                 __threadfence();
                 FenceProxyAsyncGlobal();
                 __syncwarp();
-                if (lane == 0) MbarArrive(out_ready);
+                if (lane == 0) MbarArrive(&out_ready[slot]);
                 if (q == 2) Stamp(p, k, 13);
             }
-        }
+        });
     }
 
     TcFenceBefore();
@@ -532,6 +557,7 @@ cudaError_t DenseBlockFp8(const DenseBlockArgs& a, cudaStream_t stream) {
     p.buf = a.buf; p.pitch = a.pitch; p.n = a.n; p.H = a.H; p.W = a.W;
     p.ipc = ipc;
     p.num_groups = (a.n + ipc - 1) / ipc;
+    { static const bool il = [] { const char* e = getenv("B200_DENSE_INTERLEAVE"); return !(e && e[0] == '0'); }(); p.interleave = il ? 1 : 0; }
     p.trace = nullptr;
     static unsigned long long* trace_buf = nullptr;
     if (getenv("B200_DENSE_TRACE")) {
