@@ -1,0 +1,118 @@
+"""Engine-arithmetic oracle for the e4m3 mode - TEST INFRASTRUCTURE ONLY (imported by tests/, never by the product).
+
+`oracle/onnx_oracle.py` restates the ONNX operators in fp32; the e4m3 engine cannot match it closely (3 mantissa bits per stored
+value), so the per-operator gate against it has to be wide.  This module restates the REDUCED-PRECISION arithmetic the engine is
+specified to perform - where every rounding happens and to which format - in numpy float64 (every product and partial sum below is
+exact in double), so that the GPU kernels can be held to a tight gate: apart from the summation order of the fp32 accumulator
+(which can move a result across an e4m3 rounding boundary once in a while) the two must agree bit for bit.
+
+The roundings (file:line of the engine code that performs them; the reference itself does all of this in fp32 inside ONNX Runtime,
+reference inference_engine/src/model.cpp:1264-1270):
+  * graph input -> e4m3, round to nearest even, saturating at +-448       (csrc/kernels_simt.cu nchw_to_nhwc_kernel)
+  * folded BatchNormalization: scale = gamma / sqrt(var + eps), shift = beta - mean * scale in double -> float
+                                                                            (csrc/plan.cpp BnConsts)
+  * A-operand prologue: x (e4m3, exact in f16) * f16(scale) + f16(shift) as ONE fused f16 operation, optional ReLU, -> e4m3
+                                                                            (csrc/umma_ptx.cuh PrologueWordFp8)
+  * pooled prologue (transitions): the four pixels' prologue results added in f16 as (p00 + p01) + (p10 + p11) -> e4m3; the 1/4
+    of the average is folded into the epilogue scale                         (csrc/umma_ptx.cuh PoolWordFp8)
+  * weights: per-output-channel scale = max|w| / 448 (float), w / scale -> e4m3     (csrc/engine.cu Replica::Replica)
+  * products exact, accumulation in fp32 (order unspecified)                 (tcgen05.mma kind::f8f6f4)
+  * epilogue: acc * (scale * out_mul) + bias as one fp32 FMA, optional ReLU, -> e4m3      (csrc/umma_ptx.cuh EpiloguePack32)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+E4M3_MAX = 448.0
+
+
+def e4m3(x: np.ndarray) -> np.ndarray:
+    """Round to the nearest e4m3 value (ties to even), saturating; returned as float64."""
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(torch.float32).clamp(-E4M3_MAX, E4M3_MAX)
+    return t.to(torch.float8_e4m3fn).to(torch.float64).numpy()
+
+
+def e4m3_from_f32_value(x64: np.ndarray) -> np.ndarray:
+    """x64 holds float32 values (as float64): convert exactly like cvt.rn.satfinite.e4m3x2.f32."""
+    return e4m3(x64)
+
+
+def f16(x: np.ndarray) -> np.ndarray:
+    """Round a double to the nearest f16 (ties to even); returned as float64."""
+    return np.asarray(x, dtype=np.float64).astype(np.float16).astype(np.float64)
+
+
+def f32(x: np.ndarray) -> np.ndarray:
+    return np.asarray(x, dtype=np.float64).astype(np.float32).astype(np.float64)
+
+
+def fold_bn(gamma, beta, mean, var, eps=1e-5):
+    """csrc/plan.cpp BnConsts: double arithmetic, results stored as float."""
+    g, b, m, v = (np.asarray(a, dtype=np.float32).astype(np.float64) for a in (gamma, beta, mean, var))
+    inv = 1.0 / np.sqrt(v + np.float64(np.float32(eps)))
+    s = g * inv
+    return f32(s), f32(b - m * s)
+
+
+def prologue(x_q: np.ndarray, scale: np.ndarray, shift: np.ndarray, relu: bool) -> np.ndarray:
+    """x_q: e4m3 values [N,C,H,W]; returns the f16 result of the fused multiply-add (before the e4m3 rounding)."""
+    s16, b16 = f16(scale)[None, :, None, None], f16(shift)[None, :, None, None]
+    y = f16(x_q * s16 + b16)        # exact product and sum in double, ONE rounding to f16 = fma.rn.f16x2
+    return np.maximum(y, 0.0) if relu else y
+
+
+def prologue_e4m3(x_q, scale, shift, relu):
+    return e4m3(prologue(x_q, scale, shift, relu))
+
+
+def pooled_prologue_e4m3(x_q, scale, shift, relu):
+    """sum over 2x2 of the prologue results, f16 adds paired by image row, then e4m3."""
+    p = prologue(x_q, scale, shift, relu)
+    top = f16(p[:, :, 0::2, 0::2] + p[:, :, 0::2, 1::2])
+    bot = f16(p[:, :, 1::2, 0::2] + p[:, :, 1::2, 1::2])
+    return e4m3(f16(top + bot))
+
+
+def pooled_prologue_generic_e4m3(x_q, scale, shift, relu):
+    """The generic gather kernel's pooled A operand (csrc/kernels_umma.cu kModePool2; transitions the TMA kernels do not take, e.g.
+    Cout = 64): fp32 FMA with the fp32 constants, the four pixels added one after the other in fp32, times 0.25, then e4m3."""
+    s32, b32 = f32(scale)[None, :, None, None], f32(shift)[None, :, None, None]
+    p = f32(x_q * s32 + b32)
+    if relu:
+        p = np.maximum(p, 0.0)
+    acc = f32(p[:, :, 0::2, 0::2] + p[:, :, 0::2, 1::2])
+    acc = f32(acc + p[:, :, 1::2, 0::2])
+    acc = f32(acc + p[:, :, 1::2, 1::2])
+    return e4m3(acc * 0.25)
+
+
+def quantise_weights(w: np.ndarray):
+    """w [Cout, Cin, R, S] float32 -> (e4m3 values as float64, per-channel dequant scale as float64 holding float32)."""
+    w32 = np.asarray(w, dtype=np.float32)
+    amax = np.abs(w32).reshape(w32.shape[0], -1).max(axis=1)
+    scale = np.where(amax > 0, amax / np.float32(448.0), np.float32(1.0)).astype(np.float32)
+    q = e4m3((w32 / scale[:, None, None, None]).astype(np.float64))   # the division is a float32 operation in the engine
+    return q, scale.astype(np.float64)
+
+
+def conv_exact(a_q: np.ndarray, w_q: np.ndarray, pad: int) -> np.ndarray:
+    """stride-1 convolution with exact products and sums (double), result rounded to fp32 like the TMEM accumulator."""
+    t = torch.nn.functional.conv2d(torch.from_numpy(a_q), torch.from_numpy(w_q), None, stride=1, padding=pad)
+    return f32(t.numpy())
+
+
+def epilogue_e4m3(acc, scale, bias, relu, out_mul=1.0):
+    s = f32(scale * np.float64(np.float32(out_mul)))[None, :, None, None]      # float32 product, as in the kernel's preamble
+    b = (np.zeros_like(scale) if bias is None else f32(bias))[None, :, None, None]
+    y = f32(acc * s + b)            # one fp32 FMA
+    if relu:
+        y = np.maximum(y, 0.0)
+    return e4m3(y)
+
+
+def e4m3_step(v: np.ndarray) -> np.ndarray:
+    """distance to the next e4m3 value above |v| (the unit in which a boundary flip shows)."""
+    a = np.maximum(np.abs(v), 2.0 ** -6)
+    e = np.floor(np.log2(a))
+    return 2.0 ** (e - 3)
