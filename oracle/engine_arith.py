@@ -116,3 +116,107 @@ def e4m3_step(v: np.ndarray) -> np.ndarray:
     a = np.maximum(np.abs(v), 2.0 ** -6)
     e = np.floor(np.log2(a))
     return 2.0 ** (e - 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------- whole network
+def bf16(x: np.ndarray) -> np.ndarray:
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(torch.float32)
+    return t.to(torch.bfloat16).to(torch.float64).numpy()
+
+
+def _conv_general(a, w, stride, pad):
+    t = torch.nn.functional.conv2d(torch.from_numpy(np.ascontiguousarray(a)), torch.from_numpy(np.ascontiguousarray(w)), None,
+                                   stride=stride, padding=pad)
+    return f32(t.numpy())
+
+
+def gap_bn_relu_f32(x_q, scale, shift, relu, slices=8):
+    """csrc/kernels_simt.cu gap_kernel: fp32 FMA + ReLU per pixel, pixels q = y, y + 8, ... summed per slice, slices summed in
+    order, times float(1 / HW)."""
+    n, c, h, w = x_q.shape
+    s32, b32 = f32(scale)[None, :, None], f32(shift)[None, :, None]
+    t = f32(x_q.reshape(n, c, h * w) * s32 + b32)
+    if relu:
+        t = np.maximum(t, 0.0)
+    total = np.zeros((n, c))
+    parts = []
+    for y in range(slices):
+        acc = np.zeros((n, c))
+        for q in range(y, h * w, slices):
+            acc = f32(acc + t[:, :, q])
+        parts.append(acc)
+    for acc in parts:
+        total = f32(total + acc)
+    inv = np.float64(np.float32(1.0) / np.float32(h * w))
+    return f32(total * inv)
+
+
+def densenet_e4m3_logits(model_path: str, x: np.ndarray) -> np.ndarray:
+    """The e4m3 engine's arithmetic for a DenseNet-style graph (the layer patterns of csrc/plan.cpp's lowering rules), images x
+    [N,3,H,W] fp32 -> logits.  Stem: bf16 operands, fp32 accumulate, bias + ReLU -> e4m3; max-pool exact; dense layers and
+    transitions as in the operator-level functions above; BN + ReLU + global average pool in fp32; classifier in fp32 (restated in
+    double: its summation order is not part of the specification, the gate on the logits allows for it)."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from tools import onnx_lite
+    g = onnx_lite.load(model_path).graph
+    init = {k: np.asarray(v, dtype=np.float32) for k, v in g.initializers.items()}
+    nodes = g.nodes
+    env = {}
+    gin = g.inputs[0].name
+    i = 0
+    while i < len(nodes):
+        n = nodes[i]
+        op = n.op_type
+        if op == "Conv" and n.inputs[0] == gin:
+            assert nodes[i + 1].op_type == "Relu"
+            w, b = init[n.inputs[1]], init[n.inputs[2]]
+            acc = _conv_general(bf16(x), bf16(w), n.attrs["strides"][0], n.attrs["pads"][0])
+            y = f32(acc + f32(b)[None, :, None, None])          # acc * 1.0 + bias, one fp32 FMA
+            env[nodes[i + 1].outputs[0]] = e4m3(np.maximum(y, 0.0))
+            i += 2
+        elif op == "MaxPool":
+            t = torch.nn.functional.max_pool2d(torch.from_numpy(env[n.inputs[0]]), n.attrs["kernel_shape"][0], n.attrs["strides"][0],
+                                               n.attrs["pads"][0])
+            env[n.outputs[0]] = t.numpy()
+            i += 1
+        elif op == "Concat":
+            env[n.outputs[0]] = np.concatenate([env[k] for k in n.inputs], axis=1)
+            i += 1
+        elif op == "BatchNormalization":
+            sc, sh = fold_bn(*(init[k] for k in n.inputs[1:5]), eps=n.attrs.get("epsilon", 1e-5))
+            assert nodes[i + 1].op_type == "Relu"
+            nxt = nodes[i + 2]
+            xin = env[n.inputs[0]]
+            if nxt.op_type == "GlobalAveragePool":
+                feat = gap_bn_relu_f32(xin, sc, sh, True)
+                env[nxt.outputs[0]] = feat[:, :, None, None]
+                assert nodes[i + 3].op_type == "Flatten" and nodes[i + 4].op_type == "Gemm"
+                gm = nodes[i + 4]
+                w, b = init[gm.inputs[1]].astype(np.float64), init[gm.inputs[2]].astype(np.float64)
+                env[gm.outputs[0]] = feat @ w.T + b
+                i += 5
+                continue
+            assert nxt.op_type == "Conv" and nxt.attrs["kernel_shape"][0] == 1
+            wq, ws = quantise_weights(init[nxt.inputs[1]])
+            bias = init[nxt.inputs[2]] if len(nxt.inputs) > 2 else None
+            after = nodes[i + 3]
+            if after.op_type == "AveragePool":       # transition: pool commuted in front of the conv, pooled operand in f16
+                a = pooled_prologue_e4m3(xin, sc, sh, True)
+                env[after.outputs[0]] = epilogue_e4m3(conv_exact(a, wq, 0), ws, bias, False, out_mul=0.25)
+            else:
+                assert after.op_type == "Relu"
+                a = prologue_e4m3(xin, sc, sh, True)
+                env[after.outputs[0]] = epilogue_e4m3(conv_exact(a, wq, 0), ws, bias, True)
+            i += 4
+        elif op == "Conv":                            # the 3x3 conv of a dense layer
+            wq, ws = quantise_weights(init[n.inputs[1]])
+            bias = init[n.inputs[2]] if len(n.inputs) > 2 else None
+            env[n.outputs[0]] = epilogue_e4m3(conv_exact(env[n.inputs[0]], wq, n.attrs["pads"][0]), ws, bias, False)
+            i += 1
+        else:
+            raise NotImplementedError(f"{op} at node {i}")
+    return env[g.outputs[0].name]
