@@ -74,9 +74,10 @@ def pooled_prologue_e4m3(x_q, scale, shift, relu):
     return e4m3(f16(top + bot))
 
 
-def pooled_prologue_generic_e4m3(x_q, scale, shift, relu):
+def pooled_prologue_generic_f32(x_q, scale, shift, relu):
     """The generic gather kernel's pooled A operand (csrc/kernels_umma.cu kModePool2; transitions the TMA kernels do not take, e.g.
-    Cout = 64): fp32 FMA with the fp32 constants, the four pixels added one after the other in fp32, times 0.25, then e4m3."""
+    Cout = 64): fp32 FMA with the fp32 constants, the four pixels added one after the other in fp32, times 0.25; the caller rounds
+    the result to the storage format."""
     s32, b32 = f32(scale)[None, :, None, None], f32(shift)[None, :, None, None]
     p = f32(x_q * s32 + b32)
     if relu:
@@ -84,7 +85,7 @@ def pooled_prologue_generic_e4m3(x_q, scale, shift, relu):
     acc = f32(p[:, :, 0::2, 0::2] + p[:, :, 0::2, 1::2])
     acc = f32(acc + p[:, :, 1::2, 0::2])
     acc = f32(acc + p[:, :, 1::2, 1::2])
-    return e4m3(acc * 0.25)
+    return acc * 0.25
 
 
 def quantise_weights(w: np.ndarray):
@@ -118,10 +119,58 @@ def e4m3_step(v: np.ndarray) -> np.ndarray:
     return 2.0 ** (e - 3)
 
 
-# ---------------------------------------------------------------------------------------------------------------- whole network
 def bf16(x: np.ndarray) -> np.ndarray:
+    """Round to the nearest bf16 (ties to even); returned as float64."""
     t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(torch.float32)
     return t.to(torch.bfloat16).to(torch.float64).numpy()
+
+
+class Bf16Mode:
+    """The same pipeline in BF16 mode: activations and weights are bf16 (no weight scale), the prologue is ONE fused bf16
+    multiply-add (fma.rn.relu.bf16x2, csrc/umma_ptx.cuh ProloguePiece<bf16>), the pooled prologue adds in bf16, the epilogue is the
+    same fp32 FMA narrowed to bf16."""
+
+    @staticmethod
+    def store(x):
+        return bf16(x)
+
+    @staticmethod
+    def prologue(x_q, scale, shift, relu):
+        s, b = bf16(scale)[None, :, None, None], bf16(shift)[None, :, None, None]
+        y = bf16(x_q * s + b)       # products of two bf16 values and the sum are exact in double: one rounding
+        return np.maximum(y, 0.0) if relu else y
+
+    @classmethod
+    def pooled_prologue(cls, x_q, scale, shift, relu):
+        p = cls.prologue(x_q, scale, shift, relu)
+        top = bf16(p[:, :, 0::2, 0::2] + p[:, :, 0::2, 1::2])
+        bot = bf16(p[:, :, 1::2, 0::2] + p[:, :, 1::2, 1::2])
+        return bf16(top + bot)
+
+    @staticmethod
+    def weights(w):
+        w32 = np.asarray(w, dtype=np.float32)
+        return bf16(w32.astype(np.float64)), np.ones(w32.shape[0])
+
+    @staticmethod
+    def epilogue(acc, scale, bias, relu, out_mul=1.0):
+        s = f32(scale * np.float64(np.float32(out_mul)))[None, :, None, None]
+        b = (np.zeros_like(scale) if bias is None else f32(bias))[None, :, None, None]
+        y = f32(acc * s + b)
+        if relu:
+            y = np.maximum(y, 0.0)
+        return bf16(y)
+
+
+class E4m3Mode:
+    store = staticmethod(e4m3)
+    prologue = staticmethod(lambda x_q, scale, shift, relu: prologue_e4m3(x_q, scale, shift, relu))
+    pooled_prologue = staticmethod(lambda x_q, scale, shift, relu: pooled_prologue_e4m3(x_q, scale, shift, relu))
+    weights = staticmethod(quantise_weights)
+    epilogue = staticmethod(epilogue_e4m3)
+
+
+# ---------------------------------------------------------------------------------------------------------------- whole network
 
 
 def _conv_general(a, w, stride, pad):

@@ -102,3 +102,35 @@ def test_densenet_graph_operator_census(densenet_path):
     assert c["Conv"] == 120 and c["BatchNormalization"] == 62 and c["Relu"] == 121 and c["Concat"] == 62
     assert c["AveragePool"] == 3 and c["MaxPool"] == 1 and c["GlobalAveragePool"] == 1 and c["Gemm"] == 1
     assert [v.name for v in m.graph.inputs] == ["data_0"] and [v.name for v in m.graph.outputs] == ["fc6_1"]
+
+
+def test_engine_arithmetic_oracle_rounding_primitives():
+    """oracle/engine_arith.py: the roundings the e4m3 / bf16 engine is specified to make (known answers)."""
+    from oracle import engine_arith as ea
+    # e4m3: 3 mantissa bits, ties to even, saturating at 448, subnormals down to 2^-9
+    assert ea.e4m3(np.array([0.3, 1.0625, 1.1875, 500.0, -1000.0, 2.0 ** -9, 2.0 ** -11])).tolist() == [0.3125, 1.0, 1.25, 448.0, -448.0, 2.0 ** -9, 0.0]
+    assert ea.bf16(np.array([1.00390625, 1.01171875])).tolist() == [1.0, 1.015625]       # ties to even, both directions
+    # the fused f16 multiply-add rounds ONCE: 0.1 (f16) * 3 + 2^-12 differs from the two-step result
+    x = np.full((1, 1, 1, 1), 3.0)
+    fused = ea.prologue(x, np.array([0.1]), np.array([2.0 ** -12]), False)[0, 0, 0, 0]
+    s16 = float(np.float16(0.1))
+    assert fused == float(np.float16(3.0 * s16 + 2.0 ** -12))
+    # per-output-channel weight quantisation: the largest weight of every row maps to 448
+    q, sc = ea.quantise_weights(np.array([[[[0.5]], [[-0.25]]], [[[2.0]], [[1.0]]]], dtype=np.float32))
+    assert q[:, :, 0, 0].tolist() == [[448.0, -224.0], [448.0, 224.0]] and np.allclose(sc * 448.0, [0.5, 2.0])
+    # pooled prologue: (p00 + p01) + (p10 + p11) in f16
+    xq = np.arange(4, dtype=np.float64).reshape(1, 1, 2, 2)
+    assert ea.pooled_prologue_e4m3(xq, np.array([1.0]), np.array([0.0]), True)[0, 0, 0, 0] == 6.0
+    assert ea.e4m3_step(np.array([1.0, 300.0])).tolist() == [0.125, 32.0]
+
+
+def test_engine_arithmetic_densenet_is_close_to_the_fp32_oracle(densenet_path):
+    """The e4m3 restatement of the whole network stays within the format's noise of the fp32 ONNX oracle (same top-1)."""
+    from oracle import engine_arith as ea
+    from tools import synth
+    x = synth.to_model_input(synth.clustered_images_u8(1, start=300))
+    q = ea.densenet_e4m3_logits(densenet_path, x)
+    f = OnnxOracle(densenet_path).run({"data_0": x})[0]
+    assert q.shape == f.shape == (1, 1000)
+    assert int(q.argmax()) == int(f.argmax())
+    assert np.abs(q - f).max() / np.abs(f).max() < 0.25
