@@ -22,6 +22,7 @@
 // No thread ever touches the activations: the producer
 // is one elected lane issuing TMA, so the whole CTA is 6 warps (TMA, MMA, 4 epilogue).  The 9 weight tiles
 // ([32][128 B] each) are TMA-loaded once and stay resident; patches stream through a ring of kBufs buffers.
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -243,6 +244,253 @@ cudaError_t LaunchC3(const CUtensorMap& tw, const CUtensorMap& tin, const C3Para
     return le;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------- CTA pairs
+// The same convolution with the two CTAs of a cluster executing ONE tcgen05.mma of M = 256 per (filter row, K step)
+// (cta_group::2): each CTA supplies its own patch view (128 rows of A) and only HALF of the stacked weight tile (48 of the 96
+// rows, at the same shared-memory offset in both CTAs).  With both operands in shared memory a dispatch is operand-fetch bound at
+// 64 B/clk (tools/ubench/mma_issue.cu): 4 KB of A + 3 KB of B = 91 cycles alone, 4 KB + 1.5 KB = 65 cycles as a pair.
+// The leader (cluster rank 0) issues the MMAs for both; its peer forwards "my patch has landed" and "my accumulator is drained"
+// to the leader's barriers, the commit multicasts "patch free" / "accumulator full" to both CTAs.  Both CTAs walk the same number
+// of steps (a peer without a tile left repeats the last one and stores nothing).  e4m3 only (one 128-byte K plane per pixel).
+constexpr int kC3PairHalfRows = kC3NS / 2;          // 48 weight rows per CTA and filter row
+constexpr int kC3PairWeightBytes = 3 * kC3PairHalfRows * 128;
+constexpr int kC3PairBufs = 6;
+constexpr int kC3PairSmemBytes = 1024 + 18 * 1024 /*weights, padded*/ + kC3PairBufs * kC3PlaneBytes + 1024 + 256;
+
+constexpr int kC3PairThreads = 320;   // 8 epilogue warps (two per TMEM lane quarter, 16 output channels each), TMA, MMA
+
+__global__ void __launch_bounds__(kC3PairThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_w16, const __grid_constant__ CUtensorMap tmap_in, const C3Params p) {
+    using MmaT = __nv_fp8_e4m3;
+    using OutT = __nv_fp8_e4m3;
+    using ME = MmaElem<MmaT>;
+    constexpr int NB = kC3PairBufs;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_w = smem;                              // [fr][48 rows][128 B]
+    uint8_t* s_patch = smem + 18 * 1024;
+    uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_patch + NB * kC3PlaneBytes + 1024);
+    uint64_t* patch_full = w_bar + 1;
+    uint64_t* patch_empty = patch_full + NB;
+    uint64_t* peer_full = patch_empty + NB;           // leader only: the peer's patch of this buffer has landed
+    uint64_t* tmem_full = peer_full + NB;
+    uint64_t* tmem_empty = tmem_full + kC3Acc;        // leader only: both CTAs' epilogues have drained the accumulator (16 warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kC3Acc);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kNW = kC3PairThreads / 32;
+    const int wrole = warp >= kNW - 2 ? warp - (kNW - 2) : warp + 2;  // 0 TMA, 1 MMA, 2..9 epilogue
+    const uint32_t rank = ClusterCtaRank();
+    const bool is_leader = rank == 0;
+    // steps of this pair: the tiles of the even CTA decide; the odd CTA may be one tile short at the very end
+    const int base = (int)(blockIdx.x & ~1u);
+    const int steps = base < p.num_tiles ? (p.num_tiles - base + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (wrole == 0 && lane == 0) {
+        MbarInit(w_bar, 1);
+        for (int b = 0; b < NB; ++b) {
+            MbarInit(&patch_full[b], 1);
+            MbarInit(&patch_empty[b], 1);
+            MbarInit(&peer_full[b], 1);
+        }
+        for (int a = 0; a < kC3Acc; ++a) {
+            MbarInit(&tmem_full[a], 1);
+            MbarInit(&tmem_empty[a], 16);
+        }
+        FenceBarrierInit();
+        PrefetchTensorMap(&tmap_w16);
+        PrefetchTensorMap(&tmap_in);
+    }
+    if (wrole == 1) TmemAlloc2(tmem_slot, kC3Acc * kC3AccStride);
+    TcFenceBefore();
+    __syncthreads();
+    ClusterSync();   // the peer's barriers exist before anything arrives on them remotely
+    TcFenceAfter();
+    const uint32_t tmem_base = *tmem_slot;
+    GridDepLaunch();
+
+    if (wrole == 0) {
+        // =========================================================== TMA producer: this CTA's half of the weights, then the patch ring
+        if (ElectOne()) {
+            MbarArriveExpectTx(w_bar, (uint32_t)kC3PairWeightBytes);
+            // stacked rows of filter row fr: [fs*32 + o]; this CTA holds rows 48*rank .. 48*rank + 47 in pieces of 16 output channels
+            for (int fr = 0; fr < 3; ++fr)
+                for (int piece = 0; piece < 3; ++piece) {
+                    const int row = (int)rank * kC3PairHalfRows + piece * 16;   // stacked row of the piece
+                    const int fs = row / 32, o0 = row % 32;
+                    TmaLoad2D(s_w + (fr * kC3PairHalfRows + piece * 16) * 128, &tmap_w16, w_bar, (fr * 3 + fs) * ME::kChunk, o0);
+                }
+        }
+        __syncwarp();
+        GridDepWait();
+        const uint32_t box_bytes = (uint32_t)((p.TH + 2) * kC3PW * 128);
+        for (int k = 0; k < steps; ++k) {
+            const uint32_t buf = (uint32_t)k % NB, par = (((uint32_t)k / NB) & 1u) ^ 1u;
+            int tile = (int)blockIdx.x + k * (int)gridDim.x;
+            if (tile >= p.num_tiles) tile = p.num_tiles - 1;
+            MbarWait(&patch_empty[buf], par);
+            if (ElectOne()) {
+                const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+                MbarArriveExpectTx(&patch_full[buf], box_bytes);
+                TmaLoad4D(s_patch + buf * kC3PlaneBytes, &tmap_in, &patch_full[buf], p.in_coff, tx * p.TW - 1, ty * p.TH - 1, img);
+            }
+            __syncwarp();
+        }
+    } else if (wrole == 1) {
+        if (!is_leader) {
+            // =========================================================== peer: forward "my patch has landed" to the leader
+            for (int k = 0; k < steps; ++k) {
+                const uint32_t buf = (uint32_t)k % NB, ph = ((uint32_t)k / NB) & 1u;
+                MbarWait(&patch_full[buf], ph);
+                if (ElectOne()) MbarArriveCluster(MapaShared(SmemAddr(&peer_full[buf]), 0));
+                __syncwarp();
+            }
+        } else {
+            // =========================================================== leader: MMA issuer for the pair
+            constexpr uint32_t idesc = MakeInstrDescM(ME::kFmt, kC3NS, 256);
+            const uint64_t b_base = MakeSmemDesc(SmemAddr(s_w));
+            const uint32_t patch_addr = SmemAddr(s_patch);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            MbarWait(w_bar, 0);
+            for (int k = 0; k < steps; ++k) {
+                const uint32_t buf = (uint32_t)k % NB, ph = ((uint32_t)k / NB) & 1u;
+                const uint32_t acc = (uint32_t)k % kC3Acc, acc_ph = ((uint32_t)k / kC3Acc) & 1u;
+                MbarWait(&tmem_empty[acc], acc_ph ^ 1u);
+                MbarWait(&patch_full[buf], ph);
+                MbarWait(&peer_full[buf], ph);
+                TcFenceAfter();
+                if (ElectOne()) {
+                    const uint32_t d_addr = tmem_u + acc * kC3AccStride;
+                    const uint32_t a_buf = patch_addr + buf * kC3PlaneBytes;
+#pragma unroll
+                    for (int fr = 0; fr < 3; ++fr) {
+                        const uint64_t a_desc = MakeSmemDesc(a_buf + fr * kC3PW * 128);
+                        const uint64_t b_desc = b_base + (uint64_t)(fr * (kC3PairHalfRows * 128 / 16));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            if (ks < p.ksteps) UmmaSS2Fp8(d_addr, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, (fr | ks) ? 1u : 0u);
+                    }
+                    UmmaCommit2(&patch_empty[buf]);
+                    UmmaCommit2(&tmem_full[acc]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =========================================================== epilogue: warp -> TMEM lane quarter e = warp & 3, channel half h
+        // (the 4-warp epilogue of the single-CTA kernel needs ~0.6 us per tile and would hide the pair's faster MMAs)
+        const int e = warp & 3, h = warp >> 2;
+        OutT* out = reinterpret_cast<OutT*>(p.out);
+        float sc[16], bi[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            sc[q] = h * 16 + q < p.Cout ? p.out_scale[h * 16 + q] : 0.f;
+            bi[q] = (p.bias && h * 16 + q < p.Cout) ? p.bias[h * 16 + q] : 0.f;
+        }
+        const int mrow = e * 32 + lane;
+        const int y = mrow / kC3PW, x = mrow - y * kC3PW;
+        const uint32_t leader_empty = MapaShared(SmemAddr(tmem_empty), 0);
+        GridDepWait();
+        for (int k = 0; k < steps; ++k) {
+            const uint32_t acc = (uint32_t)k % kC3Acc, acc_phase = ((uint32_t)k / kC3Acc) & 1u;
+            const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+            const bool live = tile < p.num_tiles;
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, img = tile / (p.tiles_x * p.tiles_y);
+            MbarWait(&tmem_full[acc], acc_phase);
+            TcFenceAfter();
+            uint32_t r0[16], r1[16], r2[16];
+            const uint32_t t_addr = tmem_base + ((uint32_t)(e * 32) << 16) + acc * kC3AccStride + (uint32_t)h * 16;
+            TmemLoad16(t_addr, r0);
+            TmemLoad16(t_addr + 32, r1);
+            TmemLoad16(t_addr + 64, r2);
+            TmemLoadWait();
+            TcFenceBefore();
+            __syncwarp();
+            if (lane == 0) MbarArriveCluster(leader_empty + acc * 8);  // one arrive per warp, on the LEADER's barrier
+            // out[m] = D[m][fs = 0] + D[m + 1][fs = 1] + D[m + 2][fs = 2]
+            float v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float a1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[c]), 1);
+                const float a2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 2);
+                v[c] = (__uint_as_float(r0[c]) + a1) + a2;
+            }
+            const int oy = ty * p.TH + y, ox = tx * p.TW + x;
+            if (live && y < p.TH && x < p.TW && oy < p.H && ox < p.W) {
+                uint32_t w[4];
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const float2 a = Fma2(make_float2(v[c], v[c + 1]), make_float2(sc[c], sc[c + 1]), make_float2(bi[c], bi[c + 1]));
+                    const float2 b = Fma2(make_float2(v[c + 2], v[c + 3]), make_float2(sc[c + 2], sc[c + 3]), make_float2(bi[c + 2], bi[c + 3]));
+                    w[c / 4] = p.post_relu ? (CvtE4m3x2<true>(a.x, a.y) | (CvtE4m3x2<true>(b.x, b.y) << 16))
+                                           : (CvtE4m3x2<false>(a.x, a.y) | (CvtE4m3x2<false>(b.x, b.y) << 16));
+                }
+                OutT* orow = out + ((size_t)(img * p.H + oy) * p.W + ox) * p.out_pitch + p.out_coff + h * 16;
+                *reinterpret_cast<uint4*>(orow) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            __syncwarp();
+        }
+    }
+    TcFenceBefore();
+    __syncthreads();
+    ClusterSync();   // neither CTA may release tensor memory (or exit with remote arrives pending) before both are done
+    if (wrole == 1) {
+        TcFenceAfter();
+        TmemDealloc2(tmem_base, kC3Acc * kC3AccStride);
+    }
+}
+
+cudaError_t LaunchC3Pair(const CUtensorMap& tw16, const CUtensorMap& tin, const C3Params& p, cudaStream_t stream) {
+    auto kern = conv3x3_pair_kernel;
+    static int sm_count[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!sm_count[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kC3PairSmemBytes);
+        if (e != cudaSuccess) return e;
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count[dev] = n > 0 ? n : 148;
+    }
+    // a persistent kernel must be fully resident: not every TPC of the chip has both SMs enabled, so ask how many pairs fit
+    static int max_pairs[64] = {0};
+    if (!max_pairs[dev]) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)(sm_count[dev] & ~1));
+        q.blockDim = dim3((unsigned)kC3Threads);
+        q.dynamicSmemBytes = kC3PairSmemBytes;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa; q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) n = sm_count[dev] / 2;
+        max_pairs[dev] = n;
+        if (getenv("B200_ENGINE_VERBOSE")) fprintf(stderr, "conv3x3 pair kernel: %d CTA pairs resident on %d SMs\n", n, sm_count[dev]);
+    }
+    int grid = (p.num_tiles + 1) & ~1;
+    if (grid > 2 * max_pairs[dev]) grid = 2 * max_pairs[dev];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)kC3PairThreads);
+    cfg.dynamicSmemBytes = kC3PairSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tw16, tin, p);
+    CountLaunch();
+    return le;
+}
+
 }  // namespace
 
 bool Conv3x3TmaSupported(const ConvArgs& a) {
@@ -290,6 +538,16 @@ cudaError_t Conv3x3Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
     const CUtensorMap& tw = *reinterpret_cast<const CUtensorMap*>(w.tensor_map);
     const CUtensorMap& ti = *reinterpret_cast<const CUtensorMap*>(&tin);
     if (it == DType::BF16) return LaunchC3<__nv_bfloat16, __nv_bfloat16>(tw, ti, p, stream);
+    // CTA pairs (cta_group::2): B200_ENGINE_C3PAIR=1; needs whole 32-channel outputs and at least one tile per CTA of a pair
+    static const bool pair_enabled = [] { const char* e = getenv("B200_ENGINE_C3PAIR"); return e && e[0] == '1'; }();
+    if (pair_enabled && a.Cout == 32 && p.num_tiles >= 2 && w.w && w.Cout_pad == 32) {
+        TensorMap tw16;
+        const uint64_t wdims[2] = {(uint64_t)w.K_pad, 32};
+        const uint64_t wstrides[1] = {(uint64_t)w.K_pad};
+        const uint32_t wbox[2] = {128u, 16u};
+        if (MakeTensorMap(&tw16, w.w, 1, 2, wdims, wstrides, wbox, true) != 0) return cudaErrorInvalidValue;
+        return LaunchC3Pair(*reinterpret_cast<const CUtensorMap*>(&tw16), ti, p, stream);
+    }
     return LaunchC3<__nv_fp8_e4m3, __nv_fp8_e4m3>(tw, ti, p, stream);
 }
 

@@ -75,7 +75,10 @@ __device__ __noinline__ void MbarTimeout() {
     printf("conv_umma: mbarrier timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
     __trap();
 }
+// (measured, tools/ubench/mbar_cost.cu: a try_wait on an ALREADY completed phase costs ~118 cycles, a test_wait 34 - so every wait
+// probes with test_wait first; in a well-fed pipeline most waits are satisfied when they are issued)
 __device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
+    if (MbarTest(bar, parity)) return;
     if (MbarTryWait(bar, parity)) return;
     uint32_t spins = 0;
     while (!MbarTryWait(bar, parity)) {
@@ -93,7 +96,7 @@ __device__ __forceinline__ void MbarWait(uint64_t* bar, uint32_t parity) {
 // phase is still pending, so 18 warps x 32 lanes polling at full speed made 30-55 % of all executed instructions
 // SYNCS polls and slowed the working warps down by up to 1.7x.
 __device__ __forceinline__ void MbarWaitWarp(uint64_t* bar, uint32_t parity) {
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0 && !MbarTest(bar, parity)) {
         uint32_t spins = 0;
         while (!MbarTryWait(bar, parity)) {
 #if B200_POLL_SLEEP_NS > 0
@@ -283,6 +286,53 @@ __device__ __forceinline__ void UmmaSS(uint32_t tmem_d, uint64_t desc_a, uint64_
 // Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void UmmaCommit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemAddr(bar)) : "memory");
+}
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster execute one tcgen05.mma of M = 256 together; each supplies its own 128 rows
+// of A and HALF of B (N / 2 rows at the same shared-memory offset in both CTAs), so the B fetch per SM halves.
+__device__ __forceinline__ uint32_t ClusterCtaRank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void ClusterSync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t MapaShared(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+// RELAXED on purpose: a release at cluster scope first waits for every earlier global store of the thread to become visible
+// (measured: 1.1 us per tile on an epilogue warp that stores its results with st.global).  What these arrives order is tensor-memory
+// reads (tcgen05.wait::ld + tcgen05.fence before) and TMA-written shared memory (complete_tx), neither of which needs it.
+__device__ __forceinline__ void MbarArriveCluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void TmemAlloc2(uint32_t* slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void TmemDealloc2(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// issued by the leader CTA (cluster rank 0) only
+__device__ __forceinline__ void UmmaSS2Fp8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once every MMA issued before it has completed
+__device__ __forceinline__ void UmmaCommit2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(SmemAddr(bar)), "h"((unsigned short)3) : "memory");
+}
+__host__ __device__ constexpr uint32_t MakeInstrDescM(int fmt, int n, int m) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t* r) {

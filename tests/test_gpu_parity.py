@@ -6,6 +6,7 @@ top-5 SET agreement on the fixed 1024-image synthetic set (gates in LOWP_GATES: 
 same definitions with its own measured floor)."""
 import json
 import os
+import sys
 import threading
 
 import numpy as np
@@ -565,6 +566,41 @@ def test_split_wide_transitions_are_bit_identical(pkg, repo_dir, monkeypatch, pr
     assert launches["2"] == launches["0"] + (3 if precision == "fp8" else 2), launches
     assert np.array_equal(outs["0"], outs["2"])
     assert launches["1"] == launches["0"] + 2, launches   # "1": the two wide transitions gained a kernel each
+    assert np.array_equal(outs["0"], outs["1"])
+
+
+def test_cta_pair_conv3x3_kernel_is_bit_identical(pkg, repo_dir, monkeypatch):
+    """B200_ENGINE_C3PAIR=1: the 3x3 convs of the 56x56 / 28x28 blocks run as CTA pairs (cta_group::2: ONE tcgen05.mma of M = 256 per
+    two patch tiles, each CTA holding half of the stacked weight tile; the peer forwards its barriers to the leader, commits are
+    multicast).  Same products, same accumulation order inside a tile: bit-identical logits, odd and even tile counts."""
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "fp8")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "16")
+    monkeypatch.setenv("B200_ENGINE_DEVICES", "0")
+    monkeypatch.setenv("B200_ENGINE_INSTANCES", "1")
+    x = synth.to_model_input(synth.synthetic_images_u8(11, start=6100))
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as ge\n"
+        "pkg = ge.load_package()\n"
+        "x = np.load(sys.argv[1])\n"
+        "mgr = pkg.InferenceManager(%r)\n"
+        "mgr.load_model('densenet_onnx'); m = mgr.get_model('densenet_onnx')\n"
+        "outs = [m.infer([pkg.TensorData('data_0', x[:n])], [pkg.OutputConfig('fc6_1', [n, 1000])])[0].data for n in (11, 1, 4)]\n"
+        "np.save(sys.argv[2], np.concatenate(outs))\n"
+        "mgr.shutdown()\n") % (ROOT, repo_dir)
+    import subprocess
+    import tempfile
+    outs = {}
+    with tempfile.TemporaryDirectory() as td:
+        np.save(os.path.join(td, "x.npy"), x)
+        for flag in ("0", "1"):   # the switch is read once per process
+            env = dict(os.environ, B200_ENGINE_C3PAIR=flag)
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(td, "x.npy"), os.path.join(td, f"y{flag}.npy")],
+                               capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[flag] = np.load(os.path.join(td, f"y{flag}.npy"))
+    assert outs["0"].shape == (16, 1000)
     assert np.array_equal(outs["0"], outs["1"])
 
 

@@ -59,6 +59,50 @@ __global__ void __launch_bounds__(128, 1) mma_issue_kernel(int n, int mode, int 
     if (warp == 1) { TcFenceAfter(); TmemDealloc(tmem, 512); }
 }
 
+
+// CTA pair (cta_group::2): M = 256 across the two CTAs of a cluster, each CTA holds N / 2 rows of B; the leader issues for both.
+__global__ void __launch_bounds__(128, 1) mma_pair_kernel(int n, int count, long long* cycles_out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_a = smem;
+    uint8_t* s_b = smem + 16384;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = ClusterCtaRank();
+    if (threadIdx.x == 0) { MbarInit(&bar, 1); FenceBarrierInit(); }
+    if (warp == 1) TmemAlloc2(&tmem_slot, 512);
+    FenceProxyAsync();
+    TcFenceBefore();
+    __syncthreads();
+    ClusterSync();
+    TcFenceAfter();
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0) {
+        const uint32_t idesc = MakeInstrDescM(0, n, 256);
+        const uint64_t a_desc = MakeSmemDesc(SmemAddr(s_a)), b_desc = MakeSmemDesc(SmemAddr(s_b));
+        long long t0 = clock64();
+        if (rank == 0) {
+            if (ElectOne()) {
+                for (int i = 0; i < count; ++i) {
+                    const int ks = i & 3;
+                    UmmaSS2Fp8(tmem, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc, i ? 1u : 0u);
+                }
+                UmmaCommit2(&bar);
+            }
+            __syncwarp();
+        }
+        MbarWaitWarp(&bar, 0);
+        long long t1 = clock64();
+        if (threadIdx.x == 0) cycles_out[blockIdx.x] = t1 - t0;
+    }
+    TcFenceBefore();
+    __syncthreads();
+    ClusterSync();
+    if (warp == 1) { TcFenceAfter(); TmemDealloc2(tmem, 512); }
+}
+
 int main() {
     int dev = 0, sms = 0, khz = 0;
     cudaGetDevice(&dev);
@@ -85,6 +129,27 @@ int main() {
         for (int i = 0; i < sms; ++i) sum += (double)h[i];
         const double cyc = sum / sms / count, nominal = 128.0 * c.n / 256.0;
         printf("%-10s %-4s %5d %5d %12.1f %12.1f %9.0f%%\n", c.kind ? "f8f6f4" : "f16(bf16)", c.mode ? "tmem" : "smem", c.n, c.accs, cyc, nominal, 100.0 * nominal / cyc);
+    }
+    cudaFuncSetAttribute(mma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int n : {32, 96, 128, 256}) {
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(sms & ~1));
+            cfg.blockDim = dim3(128);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, mma_pair_kernel, n, count, d_cyc);
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("pair launch failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+        long long h[256];
+        cudaMemcpy(h, d_cyc, (sms & ~1) * sizeof(long long), cudaMemcpyDeviceToHost);
+        double sum = 0; int cnt = 0;
+        for (int i = 0; i < (sms & ~1); i += 2) { sum += (double)h[i]; ++cnt; }
+        const double cyc = sum / cnt / count, nominal = 128.0 * n / 256.0;
+        printf("%-10s %-4s %5d %5s %12.1f %12.1f %9.0f%%   (cta_group::2, M = 256: per-SM nominal)\n", "f8f6f4", "pair", n, "1", cyc, nominal, 100.0 * nominal / cyc);
     }
     return 0;
 }
