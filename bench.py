@@ -600,11 +600,13 @@ def main():
                     "how": "achieved = 5.668 GFLOP/image (SURVEY.md 8d) x batch / ms_per_step (CUDA events on the engine's stream, per GPU)",
                     "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                             "algorithmic_bytes_per_image": BYTES_PER_IMAGE[args.precision], "peak_source": peaks["source"] + " (MEASURED_PEAKS.json)"},
-                    "limiter": "neither roofline as such: (1) tcgen05.mma with both operands in shared memory is operand-fetch bound at 64 B/clk "
-                               "(measured, tools/ubench/mma_issue.cu: N=96 91 cycles, N=128 107 cycles per dispatch against nominal 48 / 64), and "
-                               "DenseNet's GEMMs have N = Cout = 128 / 32 - the 3x3 kernels sit on that floor; (2) the 1x1 kernels of blocks 1-2 stream "
-                               "at ~4.8 TB/s of HBM traffic plus a fixed ~10 us per launch; (3) the 14x14 / 7x7 blocks are a per-layer dependency chain "
-                               "(MMA execution -> epilogue -> MMA); see profiles/ and DESIGN.md sections 5 and 10",
+                    "limiter": "no single saturated resource (ncu, conv3x3 block 1: DRAM 37 %, tensor pipe 46 %, L2 28 %, issue 31 %). Measured "
+                               "facts (tools/ubench, profiles/r02q_ubench_*): tcgen05.mma with both operands in shared memory is operand-fetch bound at "
+                               "64 B/clk - N=96 91 cycles, N=128 107 cycles per dispatch against nominal 48 / 64, and DenseNet's GEMMs have N = Cout = "
+                               "128 / 32; CTA pairs (cta_group::2) or an A operand in tensor memory restore the nominal rate, but neither made the 3x3 or "
+                               "the fused dense-layer kernel faster, so the convs are not tensor-bound either; the 1x1 kernels of blocks 1-2 stream at "
+                               "~4.8 TB/s of HBM traffic plus a fixed ~10 us per launch; the 14x14 / 7x7 blocks are a per-layer dependency chain "
+                               "(epilogue 1 -> 3x3 MMAs -> epilogue 2 + fences). See DESIGN.md sections 5 and 10",
                     "families_ms": {k: round(v["ms"], 4) for k, v in fam.items()},
                     "families_sum_ms": fam_ms,
                     "families_note": "per-step events WITHOUT programmatic-launch overlap; they sum to more than ms_per_step"}

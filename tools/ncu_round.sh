@@ -21,8 +21,8 @@ done
 cap fp8 c1x1_cin224 'conv1x1_tma_kernel' 5
 cap fp8 c3x3_b1 'conv3x3_tma_kernel' 5
 cap fp8 c3x3_b2 'conv3x3_tma_kernel' 17
-cap fp8 dense_b3 'dense_block_kernel<2>' 0
-cap fp8 dense_b4 'dense_block_kernel<1>' 0
+cap fp8 dense_b3 'dense_block_kernel' 0
+cap fp8 dense_b4 'dense_block_kernel' 1
 cap fp8 stem 'stem_conv7x7_kernel' 0
 cap fp8 maxpool 'maxpool3x3s2_kernel' 0
 cap fp8 poolbn_t1 'pool_bn_relu_2x2_kernel' 0
