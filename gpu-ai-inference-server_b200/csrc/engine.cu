@@ -457,7 +457,15 @@ void Replica::BuildDenseRuns() {
             kernels::DenseLayerDesc d;
             memset(&d, 0, sizeof(d));
             memcpy(&d.w1, prepared_[j].umma.tensor_map, sizeof(CUtensorMap));
-            memcpy(&d.w2, prepared_[j + 1].umma.tensor_map, sizeof(CUtensorMap));
+            {   // the nine 3x3 taps as ONE box: dims {128 B of K inside a tap, 32 output channels, 9 taps} -> lands as [tap][row][128 B]
+                const kernels::UmmaWeights& uw = prepared_[j + 1].umma;
+                const uint64_t wdims[3] = {128, 32, 9};
+                const uint64_t wstrides[2] = {(uint64_t)uw.K_pad, 128};
+                const uint32_t wbox[3] = {128u, 32u, 9u};
+                if (uw.K_pad != 9 * 128 || uw.Cout_pad != 32 ||
+                    kernels::MakeTensorMap(&d.w2, uw.w, 1, 3, wdims, wstrides, wbox, true) != 0)
+                    throw CudaError("dense block: cannot describe the 3x3 weights of '" + b.name + "' as one TMA box");
+            }
             // folded BN1 as packed f16x2 pairs (the transform warps' arithmetic type in e4m3 mode)
             const std::vector<float>& sc = P.consts[a.pre_scale].data;
             const std::vector<float>& sh = P.consts[a.pre_shift].data;

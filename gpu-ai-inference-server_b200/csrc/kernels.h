@@ -96,7 +96,7 @@ cudaError_t PoolBnRelu2x2(View in, View out, int n, const float* scale, const fl
 // ---- a whole dense block in one persistent kernel (kernels_dense.cu; e4m3, whole images per CTA) ----
 struct DenseLayerDesc {          // one BN-ReLU-Conv1x1(->128)-BN-ReLU-Conv3x3(->32) layer; lives in device memory
     TensorMap w1;                // conv1 weights [128][K_pad] e4m3, box {128, 128}, SWIZZLE_128B
-    TensorMap w2;                // conv2 weights [32][9*128] e4m3, box {128, 32}, SWIZZLE_128B
+    TensorMap w2;                // conv2 weights [32][9*128] e4m3 seen as {128 B, 32 rows, 9 taps}, box = all of it, SWIZZLE_128B
     const uint32_t* pre_scale;   // folded BN1 scale/shift as packed f16x2 pairs, Cin/2 words each
     const uint32_t* pre_shift;
     const float* s1;             // conv1 epilogue: per-channel dequant scale, bias (BN2 folded) [128]

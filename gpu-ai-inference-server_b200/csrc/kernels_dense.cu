@@ -67,6 +67,12 @@ __device__ __forceinline__ void TmaLoad2DGlobalMap(void* smem_dst, const void* m
         ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void TmaLoad3DGlobalMap(void* smem_dst, const void* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(SmemAddr(smem_dst)), "l"((uint64_t)map), "r"(SmemAddr(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void FenceProxyAsyncGlobal() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 __device__ __forceinline__ void Stamp(const DbParams& p, uint32_t k, int ev) {
@@ -115,7 +121,7 @@ __device__ __forceinline__ void DbWalk(const DbParams& p, F&& f) {
 
 template <int MT1>
 __global__ void __launch_bounds__(kDbThreads, 1)
-dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p) {
+dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p) {   // tmap_x: box {128 B, MT1 * 128 rows}
     using MmaT = __nv_fp8_e4m3;
     using ME = MmaElem<MmaT>;
     using Cfg = DbCfg<MT1>;
@@ -204,8 +210,8 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                     const DbGeom g = DbGeomOf(c, Cin);
                     uint8_t* dst = smem + stage * Cfg::kStageBytes;
                     MbarArriveExpectTx(&raw_full[stage], (uint32_t)Cfg::kStageBytes);
-#pragma unroll
-                    for (int t = 0; t < MT1; ++t) TmaLoad2D(dst + t * kATileBytes, &tmap_x, &raw_full[stage], g.ch_base, row0 + t * kTileM);
+                    // ONE box for all MT1 A tiles (a TMA instruction costs the unit ~700 cycles whatever its size, tools/ubench/tma_rate.cu)
+                    TmaLoad2D(dst, &tmap_x, &raw_full[stage], g.ch_base, row0);
                     TmaLoad2DGlobalMap(dst + MT1 * kATileBytes, &L->w1, &raw_full[stage], g.ch_base, 0);
                 }
                 __syncwarp();
@@ -216,7 +222,7 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
             MbarWaitWarp(w2_empty, (k & 1u) ^ 1u);
             if (ElectOne()) {
                 MbarArriveExpectTx(w2_full, (uint32_t)kDbW2Bytes);
-                for (int t = 0; t < 9; ++t) TmaLoad2DGlobalMap(s_w2 + t * 32 * 128, &L->w2, w2_full, t * kDbCH, 0);
+                TmaLoad3DGlobalMap(s_w2, &L->w2, w2_full, 0, 0, 0);   // all nine taps: box {128 B, 32 rows, 9 taps}
             }
             __syncwarp();
             ++units_of[slot];
@@ -569,7 +575,7 @@ cudaError_t DenseBlockFp8(const DenseBlockArgs& a, cudaStream_t stream) {
     const uint64_t rows = (uint64_t)a.n * a.H * a.W;
     const uint64_t dims[2] = {(uint64_t)a.pitch, rows};
     const uint64_t strides[1] = {(uint64_t)a.pitch};
-    const uint32_t box[2] = {128u, (uint32_t)kTileM};
+    const uint32_t box[2] = {128u, (uint32_t)(mt1 * kTileM)};
     if (MakeTensorMap(&tx, a.buf, 1, 2, dims, strides, box, true) != 0) return cudaErrorInvalidValue;
     const CUtensorMap& t = *reinterpret_cast<const CUtensorMap*>(&tx);
     cudaError_t le = mt1 == 2 ? LaunchDb<2>(t, p, stream) : LaunchDb<1>(t, p, stream);
