@@ -504,13 +504,16 @@ void Replica::BuildDenseRuns() {
 
 // Dense layers of the large-image blocks (56x56, 28x28; e4m3): the (1x1 conv, 3x3 conv) step pair can run as ONE streaming kernel
 // that keeps the 128-channel bottleneck in shared memory (kernels_dense_stream.cu).  Bit-identical to the kernel pair and half the
-// HBM traffic, but measured SLOWER at bs256 (2.20 ms against 2.00 ms per forward; both are bound by the per-instruction cost of
-// small-N tcgen05.mma and by the tcgen05.ld rate), so it is opt-in: B200_ENGINE_LAYERFUSE=1.
+// HBM traffic.  Measured per layer at bs256 (tools/perlayer_fuse.py): the streaming kernel wins where the layer has ONE K chunk
+// (56x56, Cin <= 128: 90-93 us against 97-102 us) and loses 0.55 us per tile for every further chunk (its row-owning transform into
+// tensor memory is a latency chain per chunk), so the default ("auto") fuses exactly those layers; B200_ENGINE_LAYERFUSE=1 fuses
+// every layer of both blocks (forward 2.20 ms against 1.98 ms), =0 none.
 void Replica::MarkStreamPairs() {
     const Plan& P = *plan_;
     if (P.precision != Precision::FP8) return;
     const char* lf = getenv("B200_ENGINE_LAYERFUSE");
-    if (!(lf && lf[0] == '1')) return;
+    const int mode = !lf ? 2 : lf[0] == '0' ? 0 : lf[0] == '1' ? 1 : 2;   // 0 off, 1 all, 2 auto
+    if (mode == 0) return;
     auto readers = [&](int tensor) {
         int c = 0;
         for (const Step& s : P.steps) c += (s.in == tensor) + (s.in2 == tensor);
@@ -537,7 +540,9 @@ void Replica::MarkStreamPairs() {
         if (pa.h_out_scale.size() != 128 || pb.h_out_scale.size() != 32) continue;
         if ((int)P.consts[a.pre_scale].data.size() < a.Cin || (int)P.consts[a.pre_shift].data.size() < a.Cin) continue;
         if (!kernels::DenseLayerStreamSupported(ain.H, ain.W, a.Cin, ain.pitch)) continue;
+        if (mode == 2 && !(ain.W == 56 && a.Cin <= 128)) continue;
         pa.stream_pair = true;
+        pa.stream_min_batch = mode == 2 ? 32 : 0;
         ++i;  // the 3x3 conv is consumed by the pair
     }
 }
@@ -654,7 +659,7 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
 
 size_t Replica::EnqueueAt(size_t i, int n, int off, unsigned u8_mask) {
     const int r = prepared_[i].fused_run;
-    if (r < 0 && prepared_[i].stream_pair) {
+    if (r < 0 && prepared_[i].stream_pair && n >= prepared_[i].stream_min_batch) {
         const Plan& P = *plan_;
         const Step& a = P.steps[i];
         const Step& b = P.steps[i + 1];

@@ -118,6 +118,7 @@ private:
         int fused_run = -1;  // index into dense_runs_ when this step starts a run executed by the dense-block kernel
         bool split_pool = false;  // wide transition: pooled BN+ReLU A operand materialised once, then a plain 1x1 conv
         bool stream_pair = false; // this 1x1 conv and the 3x3 conv after it run as ONE streaming dense-layer kernel (kernels_dense_stream.cu)
+        int stream_min_batch = 0; // ... for batches of at least this many samples (auto mode: below it the kernel pair is as fast)
         std::vector<float> h_out_scale;  // host copy of umma.out_scale (kernel-parameter constants of the streaming kernel)
     };
     // Consecutive (1x1 conv, 3x3 conv) step pairs of one dense block executed by ONE persistent kernel.

@@ -605,33 +605,39 @@ def test_cta_pair_conv3x3_kernel_is_bit_identical(pkg, repo_dir, monkeypatch):
 
 
 def test_streaming_dense_layer_kernel_is_bit_identical(pkg, repo_dir, monkeypatch):
-    """B200_ENGINE_LAYERFUSE=1: every dense layer of the 56x56 / 28x28 blocks (1x1 conv -> 128 -> 3x3 conv -> 32) runs as ONE
+    """B200_ENGINE_LAYERFUSE: dense layers of the 56x56 / 28x28 blocks (1x1 conv -> 128 -> 3x3 conv -> 32) run as ONE
     streaming kernel (kernels_dense_stream.cu: bottleneck in shared memory, conv1 A operand through tensor memory, tap-stacked
     conv2, TMA-stored output) instead of the conv1x1_tma + conv3x3_tma pair.  Same arithmetic, same accumulation order: the logits
-    must be bit-identical, for whole and partial strips (batch sizes that split images across CTAs differently)."""
+    must be bit-identical, for whole and partial strips (batch sizes that split images across CTAs differently).  "1" fuses every
+    layer of both blocks, the default ("auto") the layers the streaming kernel is faster for - 56x56 with one K chunk - from 32
+    samples on."""
     monkeypatch.setenv("B200_ENGINE_PRECISION", "fp8")
-    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "16")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "32")
     monkeypatch.setenv("B200_ENGINE_DEVICES", "0")
     monkeypatch.setenv("B200_ENGINE_INSTANCES", "1")
     x = synth.to_model_input(synth.synthetic_images_u8(13, start=5200))
+    x32 = np.concatenate([x, x, x])[:32]
     outs, launches = {}, {}
-    for flag in ("0", "1"):
+    for flag in ("0", "1", "auto"):
         monkeypatch.setenv("B200_ENGINE_LAYERFUSE", flag)
         mgr = pkg.InferenceManager(repo_dir)
         try:
             mgr.load_model("densenet_onnx")
             m = mgr.get_model("densenet_onnx")
             res = {}
-            for n in (13, 1, 6):
+            for n in (13, 1, 6, 32):
+                xin = x32 if n == 32 else x[:n]
                 n0 = pkg.kernel_launch_count()
-                res[n] = m.infer([pkg.TensorData("data_0", x[:n])], [pkg.OutputConfig("fc6_1", [n, 1000])])[0].data.copy()
+                res[n] = m.infer([pkg.TensorData("data_0", xin)], [pkg.OutputConfig("fc6_1", [n, 1000])])[0].data.copy()
                 launches[(flag, n)] = pkg.kernel_launch_count() - n0
             outs[flag] = res
         finally:
             mgr.shutdown()
-    for n in (13, 1, 6):
+    for n in (13, 1, 6, 32):
         assert launches[("1", n)] == launches[("0", n)] - 18, launches   # 6 + 12 layer pairs became one launch each
+        assert launches[("auto", n)] == launches[("0", n)] - (3 if n >= 32 else 0), launches  # block 1, Cin = 64 / 96 / 128
         assert np.array_equal(outs["0"][n], outs["1"][n]), n
+        assert np.array_equal(outs["0"][n], outs["auto"][n]), n
 
 
 def test_request_coalescer_batches_concurrent_callers(pkg, repo_dir, monkeypatch):
