@@ -594,7 +594,7 @@ def main():
         fam_ms = sum(a["ms"] for a in fam.values())
         roofline = {"bound": "tensor",
                     "kernel": f"whole forward: one CUDA graph of {int(launches) // max(1, args.steps)} launches of the engine's own kernels "
-                              "(stem_conv7x7 / conv1x1_tma / conv3x3_tma / dense_block / pool_bn_relu / maxpool / gap / fc)",
+                              "(stem_conv7x7 / conv1x1_tma / conv3x3_tma / dense_stream / dense_block / pool_bn_relu / maxpool / gap / fc)",
                     "achieved": tfl, "peak": tensor_peak, "unit": "TFLOP/s", "frac": tfl / tensor_peak,
                     "peak_source": tensor_note, "traffic": traffic, "traffic_source": traffic_src,
                     "how": "achieved = 5.668 GFLOP/image (SURVEY.md 8d) x batch / ms_per_step (CUDA events on the engine's stream, per GPU)",
