@@ -132,7 +132,10 @@ __device__ __forceinline__ void DsWalk(int g0, int g1, int gpi, F1&& on_conv1, F
     if (pend) on_conv2(pend_k, pend_img, pend_og);
 }
 
-template <int HV>
+// TSA: the conv1 A operand goes through tensor memory (row-owning transform, tcgen05.st; best with ONE K chunk);
+// !TSA: the transform rewrites the landed tile in place (a warp owns one 16-byte piece of all 128 rows, as in kernels_conv1x1.cu) and
+// the conv1 MMAs read A from shared memory - a chunk then costs a fifth of the row-owning transform's latency chain.
+template <int HV, bool TSA>
 __global__ void __launch_bounds__(kDsThreads, 1)
 dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out,
@@ -165,7 +168,8 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint64_t* acc2_full = patch_full + 2;
     uint64_t* acc2_empty = acc2_full + 1;
     uint64_t* w_bar = acc2_empty + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+    uint64_t* xf_full = w_bar + 1;                // [kDsMaxStages], !TSA only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_full + kDsMaxStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // this CTA's share of the row groups
@@ -175,7 +179,8 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     if (warp == kDsTmaWarp && lane == 0) {
         for (int s = 0; s < NS; ++s) {
             MbarInit(&raw_full[s], 1);
-            MbarInit(&raw_empty[s], kDsXfWarps);
+            MbarInit(&raw_empty[s], TSA ? kDsXfWarps : 1);   // TSA: freed by the transform warps; else by the MMA commit
+            MbarInit(&xf_full[s], kDsXfWarps);
         }
         for (int s = 0; s < kDsABufs; ++s) {
             MbarInit(&a_full[s], kDsXfWarps);
@@ -242,8 +247,9 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const uint32_t patch_addr = SmemAddr(s_patch);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         MbarWaitWarp(w_bar, 0);
-        int ab = 0;
-        uint32_t aphase = 0, d = 0;
+        int ab = 0, mstage = 0;
+        uint32_t aphase = 0, mphase = 0, d = 0;
+        const uint64_t raw_desc = MakeSmemDesc(SmemAddr(s_raw));
         DsWalk<RPT>(g0, g1, p.gpi,
             [&](uint32_t k, int, int) {
                 // conv1 of tile k: its accumulator must have been drained by epilogue 1 of tile k-2
@@ -255,15 +261,30 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     const DsGeom g = DsGeomOf(c, Cin);
                     const int ks_lo = g.k_lo / ME::kStepK, ks_hi = g.k_hi / ME::kStepK;
                     const uint64_t b_desc = w1_desc + (uint64_t)((uint32_t)c * ((128 * kRowBytes) >> 4));
-                    MbarWaitWarp(&a_full[ab], aphase);
-                    TcFenceAfter();
-                    if (ElectOne()) {
+                    if (TSA) {
+                        MbarWaitWarp(&a_full[ab], aphase);
+                        TcFenceAfter();
+                        if (ElectOne()) {
 #pragma unroll
-                        for (int ks = 0; ks < kDsCH / ME::kStepK; ++ks)
-                            if (ks >= ks_lo && ks < ks_hi)
-                                UmmaTS(d1, tmem_u + kDsACol + ab * 32 + ks * 8, b_desc + (uint64_t)(2 * ks), idesc1, (c > 0 || ks > ks_lo) ? 1u : 0u);
-                        UmmaCommit(&a_empty[ab]);
-                        if (c == nc - 1) UmmaCommit(&acc1_full[k & 1u]);
+                            for (int ks = 0; ks < kDsCH / ME::kStepK; ++ks)
+                                if (ks >= ks_lo && ks < ks_hi)
+                                    UmmaTS(d1, tmem_u + kDsACol + ab * 32 + ks * 8, b_desc + (uint64_t)(2 * ks), idesc1, (c > 0 || ks > ks_lo) ? 1u : 0u);
+                            UmmaCommit(&a_empty[ab]);
+                            if (c == nc - 1) UmmaCommit(&acc1_full[k & 1u]);
+                        }
+                    } else {
+                        MbarWaitWarp(&xf_full[mstage], mphase);
+                        TcFenceAfter();
+                        if (ElectOne()) {
+                            const uint64_t a_desc = raw_desc + (uint64_t)((uint32_t)mstage * (kATileBytes >> 4));
+#pragma unroll
+                            for (int ks = 0; ks < kDsCH / ME::kStepK; ++ks)
+                                if (ks >= ks_lo && ks < ks_hi)
+                                    UmmaSS<ME::kKind>(d1, a_desc + (uint64_t)(2 * ks), b_desc + (uint64_t)(2 * ks), idesc1, (c > 0 || ks > ks_lo) ? 1u : 0u);
+                            UmmaCommit(&raw_empty[mstage]);
+                            if (c == nc - 1) UmmaCommit(&acc1_full[k & 1u]);
+                        }
+                        if (++mstage == NS) { mstage = 0; mphase ^= 1u; }
                     }
                     __syncwarp();
                     if (c == nc - 1) DsStamp(p, k, 5);
@@ -292,6 +313,52 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 DsStamp(p, k, 6);
                 ++d;
             });
+    } else if (warp < kDsXfWarps && !TSA) {
+        // =========================================================== transform warps, in place: warp tw owns 16-byte piece tw of all 128 rows
+        const int tw = warp;
+        uint32_t off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = i * 32 + lane;
+            off[i] = (uint32_t)(row * kRowBytes + ((tw ^ (row & 7)) << 4));
+        }
+        const uint32_t raw_base = SmemAddr(s_raw);
+        const bool relu = p.pre_relu != 0;
+        int stage = 0;
+        uint32_t phase = 0;
+        DsWalk<RPT>(g0, g1, p.gpi,
+            [&](uint32_t k, int, int) {
+                for (int c = 0; c < nc; ++c) {
+                    const DsGeom g = DsGeomOf(c, Cin);
+                    const int p_lo = g.k_lo / EPV, p_hi = g.k_hi / EPV;
+                    const uint32_t a_base = raw_base + stage * kATileBytes;
+                    const bool mine = tw >= p_lo && tw < p_hi;
+                    uint32_t sc[8], sh[8];
+                    if (mine) {
+                        const uint32_t ca = cst_addr + (uint32_t)((g.ch_base + tw * EPV) * 2);
+                        const uint4 s0 = LdsV4(ca), s1 = LdsV4(ca + 16), h0 = LdsV4(ca + 1024), h1 = LdsV4(ca + 1040);
+                        sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                        sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+                    }
+                    MbarWaitWarp(&raw_full[stage], phase);
+                    if (c == 0 && warp == 0) DsStamp(p, k, 1);
+                    if (mine) {
+                        uint4 v[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = LdsV4(a_base + off[i]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[i] = relu ? ProloguePiece<MmaT, true>(v[i], sc, sh) : ProloguePiece<MmaT, false>(v[i], sc, sh);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) StsV4(a_base + off[i], v[i]);
+                    }
+                    FenceProxyAsync();
+                    __syncwarp();
+                    if (lane == 0) MbarArrive(&xf_full[stage]);
+                    if (c == nc - 1 && warp == 0) DsStamp(p, k, 3);
+                    if (++stage == NS) { stage = 0; phase ^= 1u; }
+                }
+            },
+            [&](uint32_t, int, int) {});
     } else if (warp < kDsXfWarps) {
         // =========================================================== transform warps: raw tile (smem) -> BN1 + ReLU -> A tile (tmem)
         // warp w owns rows 32*(w&3)..+31 (its TMEM lane quarter) and the 16-byte pieces 4*(w>>2)..+3 of them
@@ -485,11 +552,11 @@ dense_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
 }
 
-template <int HV>
+template <int HV, bool TSA>
 cudaError_t LaunchDs(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& tout, const DsConsts& cst,
                      DsParams p, cudaStream_t stream) {
     using Cfg = DsCfg<HV>;
-    auto kern = dense_stream_kernel<HV>;
+    auto kern = dense_stream_kernel<HV, TSA>;
     static int sm_count[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -568,7 +635,11 @@ cudaError_t DenseLayerStreamFp8(const DenseLayerStreamArgs& a, cudaStream_t stre
     const CUtensorMap& t = *reinterpret_cast<const CUtensorMap*>(&tx);
     const CUtensorMap& tw1 = *reinterpret_cast<const CUtensorMap*>(a.w1_map);
     const CUtensorMap& tw2 = *reinterpret_cast<const CUtensorMap*>(a.w2_map);
-    cudaError_t le = hv == 2 ? LaunchDs<2>(t, tw1, tw2, tout, cst, p, stream) : LaunchDs<1>(t, tw1, tw2, tout, cst, p, stream);
+    // one K chunk: A through tensor memory; more: in-place transform + shared-memory A (B200_ENGINE_LAYERFUSE_TSA=0/1 forces one)
+    static const int tsa_env = [] { const char* e = getenv("B200_ENGINE_LAYERFUSE_TSA"); return e ? atoi(e) : -1; }();
+    const bool tsa = tsa_env >= 0 ? tsa_env != 0 : a.Cin <= kDsCH;
+    cudaError_t le = hv == 2 ? (tsa ? LaunchDs<2, true>(t, tw1, tw2, tout, cst, p, stream) : LaunchDs<2, false>(t, tw1, tw2, tout, cst, p, stream))
+                             : (tsa ? LaunchDs<1, true>(t, tw1, tw2, tout, cst, p, stream) : LaunchDs<1, false>(t, tw1, tw2, tout, cst, p, stream));
     if (p.trace && le == cudaSuccess) {  // debug only: dump the timeline of one CTA
         cudaStreamSynchronize(stream);
         static unsigned long long host[48 * 16];
