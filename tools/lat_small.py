@@ -1,3 +1,5 @@
+"""Device-resident p50 latency of one e4m3 forward at batch 1..64 (A/B runs of a kernel-selection switch, e.g. B200_ENGINE_LAYERFUSE).
+usage (under gpurun): B200_ENGINE_LAYERFUSE=0 python tools/lat_small.py"""
 import os, sys
 ROOT='/root/repo'; sys.path.insert(0, ROOT)
 import numpy as np

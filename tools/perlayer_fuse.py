@@ -1,3 +1,7 @@
+"""Per-layer comparison of the streaming dense-layer kernel with the conv1x1 + conv3x3 kernel pair (blocks 1-2, e4m3).
+usage (under gpurun):
+  B200_ENGINE_LAYERFUSE=0 PROF_TAG=pl0 python tools/prof_steps.py fp8 256 10; B200_ENGINE_LAYERFUSE=1 PROF_TAG=pl1 python tools/prof_steps.py fp8 256 10
+  python tools/perlayer_fuse.py gpurun_out/pl0_steps_fp8_bs256.json gpurun_out/pl1_steps_fp8_bs256.json"""
 import json, sys
 a=json.load(open(sys.argv[1])); b=json.load(open(sys.argv[2]))
 # a: default (pair of kernels), b: fused (time on the 1x1 step, ~0 on the 3x3)
