@@ -624,6 +624,9 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
             a.in_u8_hwc = u8;
             a.splitk_scratch = splitk_scratch_;
             a.splitk_bytes = splitk_bytes_;
+            a.h_bias = s.bias >= 0 ? plan_->consts[s.bias].data.data() : nullptr;
+            kernels::UmmaWeights uw = pr0.umma;
+            uw.h_out_scale = pr0.h_out_scale.empty() ? nullptr : pr0.h_out_scale.data();
             if (pr0.split_pool) {
                 kernels::View src = vin;
                 src.C = s.Cin;
@@ -635,10 +638,10 @@ void Replica::EnqueueStep(size_t i, int n, int off, unsigned u8_mask) {
                 a.in = pooled;
                 a.pre_scale = a.pre_shift = nullptr;
                 a.pre_relu = false; a.pool2 = false; a.out_mul = 0.25f;
-                e = pr0.use_f32x3 ? kernels::ConvF32x3(a, pr0.umma, stream_) : kernels::Conv1x1Tma(a, pr0.umma, stream_);
+                e = pr0.use_f32x3 ? kernels::ConvF32x3(a, pr0.umma, stream_) : kernels::Conv1x1Tma(a, uw, stream_);
                 break;
             }
-            e = pr0.use_umma ? kernels::ConvUmma(a, pr0.umma, stream_)
+            e = pr0.use_umma ? kernels::ConvUmma(a, uw, stream_)
                 : pr0.use_f32x3 ? kernels::ConvF32x3(a, pr0.umma, stream_)
                                 : kernels::ConvSimtF32(a, pr0.w_kn, stream_);
             break;

@@ -32,6 +32,7 @@ struct ConvArgs {
     const float* pre_shift = nullptr;
     bool pre_relu = false;
     const float* bias = nullptr;  // [Cout]
+    const float* h_bias = nullptr;  // host copy of `bias` (optional; kernels that take their constants as kernel parameters)
     bool post_relu = false;
     bool pool2 = false;  // A rows are 2x2 averages of (prologue-transformed) input pixels
     void* splitk_scratch = nullptr;  // fp32 SIMT path: partial sums + tile counters for split-K on small batches (optional)
@@ -55,6 +56,7 @@ cudaError_t ConvSimtF32(const ConvArgs& a, const float* w_kn, cudaStream_t strea
 struct UmmaWeights {
     const void* w = nullptr;        // [Cout_pad][K_pad] in the MMA element type, K-major, zero padded
     const float* out_scale = nullptr;  // [Cout] per-output-channel dequant scale (1.0 for bf16)
+    const float* h_out_scale = nullptr;  // host copy of `out_scale` (optional)
     int K_pad = 0;                  // padded K (multiple of the 128-byte K chunk)
     int Cout_pad = 0;
     void* tensor_map = nullptr;     // device-visible CUtensorMap* (host memory, passed by value at launch)
