@@ -118,6 +118,19 @@ __device__ __forceinline__ void DbWalk(const DbParams& p, F&& f) {
             for (int l = 0; l < p.num_layers; ++l) f(k++, g, l, 0);
     }
 }
+// Layer of the unit that FOLLOWS unit (grp, l, slot) in DbWalk's order, or -1 after the last one.
+__device__ __forceinline__ int DbNextLayer(const DbParams& p, int grp, int l, int slot) {
+    const int stride = (int)gridDim.x;
+    if (p.interleave) {
+        const int ga = slot == 0 ? grp : grp - stride;            // first group of the pair
+        const bool two = ga + stride < p.num_groups;
+        if (slot == 0 && two) return l;                              // the other group, same layer
+        if (l + 1 < p.num_layers) return l + 1;
+        return ga + 2 * stride < p.num_groups ? 0 : -1;              // next pair starts at layer 0
+    }
+    if (l + 1 < p.num_layers) return l + 1;
+    return grp + stride < p.num_groups ? 0 : -1;
+}
 
 template <int MT1>
 __global__ void __launch_bounds__(kDbThreads, 1)
@@ -403,13 +416,18 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
             {
                 const DenseLayerDesc* L = p.layers + l;
                 float* vec = s_vec + (k & 1u) * 320;
-                // per-channel vectors of this layer -> shared memory (double buffered by unit parity)
-                vec[et] = L->s1[et];
-                vec[128 + et] = L->b1 ? L->b1[et] : 0.f;
-                if (et < 32) {
-                    vec[256 + et] = L->s2[et];
-                    vec[288 + et] = L->b2 ? L->b2[et] : 0.f;
-                }
+                // per-channel vectors of a layer -> shared memory, double buffered by unit parity.  The vectors of unit k + 1 are
+                // fetched while this unit waits for its 3x3 MMAs (below): at the start of a unit the global-load latency would sit on
+                // the epilogue warps' chain
+                auto load_vec = [&](const DenseLayerDesc* Lx, float* v) {
+                    v[et] = Lx->s1[et];
+                    v[128 + et] = Lx->b1 ? Lx->b1[et] : 0.f;
+                    if (et < 32) {
+                        v[256 + et] = Lx->s2[et];
+                        v[288 + et] = Lx->b2 ? Lx->b2[et] : 0.f;
+                    }
+                };
+                if (k == 0) load_vec(L, vec);
                 NamedBarSync(1, kDbEpiThreads);
                 const uint32_t vaddr = SmemAddr(vec);
                 // ---- epilogue 1: conv1 accumulators -> BN2 + ReLU -> e4m3 -> swizzled patch rows
@@ -441,6 +459,10 @@ dense_block_kernel(const __grid_constant__ CUtensorMap tmap_x, const DbParams p)
                     MbarArrive(patch_full);
                 }
                 if (q == 2) Stamp(p, k, 9);
+                {   // the next unit's vectors (its buffer was last read by epilogue 2 of unit k - 1, long finished)
+                    const int ln = DbNextLayer(p, grp, l, slot);
+                    if (ln >= 0) load_vec(p.layers + ln, s_vec + ((k + 1u) & 1u) * 320);
+                }
                 // ---- epilogue 2: conv2 accumulators -> scale -> e4m3 -> the layer's 32-channel slice of the block buffer
 #pragma unroll 1
                 for (int t = 0; t < 2; ++t) {
