@@ -508,7 +508,8 @@ cudaError_t Conv1x1Tma(const ConvArgs& a, const UmmaWeights& w, cudaStream_t str
     static const bool resb_enabled = [] { const char* e = getenv("B200_ENGINE_RESB"); return !(e && e[0] == '0'); }();
     const bool resb = resb_enabled && p.num_n_tiles == 1 && p.num_chunks <= kL1ResChunks;
     static const bool cstp_enabled = [] { const char* e = getenv("B200_ENGINE_L1CSTP"); return !(e && e[0] == '0'); }();
-    const bool cstp = cstp_enabled && resb && a.Cout == 128 && w.h_out_scale && (a.h_bias || !a.bias);
+    // (only where there is throughput to win: at a handful of tiles per launch the 1 KB of extra parameters costs launch latency)
+    const bool cstp = cstp_enabled && resb && a.Cout == 128 && w.h_out_scale && (a.h_bias || !a.bias) && p.num_m_tiles >= 148;
     L1Consts cst;
     if (cstp)
         for (int i = 0; i < 128; ++i) {

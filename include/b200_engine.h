@@ -22,6 +22,7 @@
  *   B200_ENGINE_LAYERFUSE=0|1|auto (e4m3: dense layers of the 56x56 / 28x28 blocks as ONE streaming kernel, kernels_dense_stream.cu;
  *   default auto = the layers it is faster for: 56x56 with one K chunk; 1 = all of both blocks, 0 = none; B200_ENGINE_LAYERFUSE_TSA=0|1
  *   forces its conv1 operand path: 1 = through tensor memory, 0 = in-place transform in shared memory),
+ *   B200_ENGINE_L1CSTP=0 (1x1 kernels: epilogue constants from shared memory instead of the kernel-parameter bank),
  *   B200_ENGINE_C3PAIR=1 (e4m3: 3x3 convs as CTA pairs, tcgen05.mma.cta_group::2), B200_DENSE_INTERLEAVE=0 (dense-block megakernel
  *   without the layer-by-layer interleave of two image groups); every variant is bit-identical to the others.
  */
