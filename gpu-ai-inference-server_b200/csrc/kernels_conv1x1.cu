@@ -349,8 +349,10 @@ conv1x1_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
                 if (Cfg::kStagingBufs == 2) BulkWaitRead<1>();
                 else BulkWaitRead<0>();
             }
+            // ONE warp waits for the accumulator, the barrier that follows (needed for the staging buffer anyway) releases the other
+            // seven: every poll of an mbarrier is a shared-memory access, and this kernel's shared-memory port is its busiest resource
+            if (ew == 0) MbarWaitWarp(&tmem_full[acc], acc_phase);
             NamedBarSync(1, kL1EpiWarps * 32);
-            MbarWaitWarp(&tmem_full[acc], acc_phase);
             TcFenceAfter();
             if (kCgs >= 2 || h == 0) {
 #pragma unroll
