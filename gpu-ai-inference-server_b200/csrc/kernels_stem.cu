@@ -198,7 +198,14 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
         // eight warps: TMEM lane quarter e = warp & 3, column half = (warp - 4) >> 2 (32 of the 64 channels each)
         const int e = warp & 3, half = (warp - 4) >> 2;
         OutT* out = reinterpret_cast<OutT*>(p.out);
-        const uint32_t sc_addr = SmemAddr(s_out_scale) + half * 128, bi_addr = SmemAddr(s_bias) + half * 128;
+        // this warp's 32 channels' scale / bias live in registers for the whole kernel: as 16-byte broadcast loads from shared memory
+        // they cost 2 wavefronts each, 256 per tile, on a kernel that is bound by the MMAs' shared-memory operand fetch
+        float sc[32], bi[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            sc[q] = s_out_scale[half * 32 + q];
+            bi[q] = s_bias[half * 32 + q];
+        }
         uint32_t tk = 0;
         for (int strip = blockIdx.x; strip < p.num_strips; strip += gridDim.x) {
             const int img = strip / p.strips_per_img, sy = strip - img * p.strips_per_img;
@@ -222,20 +229,19 @@ __global__ void __launch_bounds__(kThreads, 1) stem_conv7x7_kernel(const __grid_
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             if (half * 32 + q * 4 >= p.Cout) continue;
-                            const float4 s4 = LdsF4(sc_addr + q * 16), b4 = LdsF4(bi_addr + q * 16);
                             float4 v;
-                            v.x = fmaf(__uint_as_float(r[4 * q]), s4.x, b4.x);
-                            v.y = fmaf(__uint_as_float(r[4 * q + 1]), s4.y, b4.y);
-                            v.z = fmaf(__uint_as_float(r[4 * q + 2]), s4.z, b4.z);
-                            v.w = fmaf(__uint_as_float(r[4 * q + 3]), s4.w, b4.w);
+                            v.x = fmaf(__uint_as_float(r[4 * q]), sc[4 * q], bi[4 * q]);
+                            v.y = fmaf(__uint_as_float(r[4 * q + 1]), sc[4 * q + 1], bi[4 * q + 1]);
+                            v.z = fmaf(__uint_as_float(r[4 * q + 2]), sc[4 * q + 2], bi[4 * q + 2]);
+                            v.w = fmaf(__uint_as_float(r[4 * q + 3]), sc[4 * q + 3], bi[4 * q + 3]);
                             if (p.post_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                             *reinterpret_cast<float4*>(orow + q * 4) = v;
                         }
                     } else {
                         constexpr int kWords = 32 * (int)sizeof(OutT) / 4;
                         uint32_t w[kWords];
-                        if (p.post_relu) EpiloguePack32Smem<OutT, true>(r, sc_addr, bi_addr, w);
-                        else EpiloguePack32Smem<OutT, false>(r, sc_addr, bi_addr, w);
+                        if (p.post_relu) EpiloguePack32<OutT, true>(r, sc, bi, w);
+                        else EpiloguePack32<OutT, false>(r, sc, bi, w);
                         constexpr int kPer = 16 / (int)sizeof(OutT);  // channels per 16-byte store
 #pragma unroll
                         for (int q = 0; q < kWords / 4; ++q)
