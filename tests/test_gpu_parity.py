@@ -202,6 +202,11 @@ def _engine_arith_reference(case, inits, x, precision):
         a = M.store(ea.pooled_prologue_generic_f32(xq, sc, sh, True))
         wq, ws = M.weights(g("w"))
         return M.epilogue(ea.conv_exact(a, wq, 0), ws, None, False)
+    if case == "stem_maxpool":      # 7x7/s2 stem straight from the fp32 image: bf16 operands in BOTH reduced modes, then the exact max-pool
+        import torch
+        acc = ea._conv_general(ea.bf16(x), ea.bf16(g("w")), 2, 3)
+        y = M.store(np.maximum(ea.f32(acc + ea.f32(g("b"))[None, :, None, None]), 0.0))
+        return torch.nn.functional.max_pool2d(torch.from_numpy(y), 3, 2, 1).numpy()
     if case in ("dense_block", "dense_block7"):
         cat = np.maximum(xq, 0.0)
         for li in range(4 if case == "dense_block7" else 3):
@@ -218,7 +223,7 @@ def _engine_arith_reference(case, inits, x, precision):
 
 @pytest.mark.parametrize("precision", ["fp8", "bf16"])
 @pytest.mark.parametrize("case", ["conv1x1_bn_relu", "conv1x1_partial_chunk", "conv1x1_ktail", "conv1x1_long", "conv3x3", "cout256",
-                                  "transition", "transition_wide", "dense_block", "dense_block7"])
+                                  "transition", "transition_wide", "dense_block", "dense_block7", "stem_maxpool"])
 def test_operator_graphs_match_the_engine_arithmetic_oracle(pkg, tmp_path, monkeypatch, case, precision):
     """The tight gate of the reduced-precision modes.  Against the fp32 ONNX oracle an e4m3 kernel can only be held to ~0.15 of
     max|y| (the format has 3 mantissa bits), which would hide a wrong K-tail column.  Against a restatement of the engine's own
