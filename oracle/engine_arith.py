@@ -200,8 +200,8 @@ def gap_bn_relu_f32(x_q, scale, shift, relu, slices=8):
     return f32(total * inv)
 
 
-def densenet_e4m3_logits(model_path: str, x: np.ndarray) -> np.ndarray:
-    """The e4m3 engine's arithmetic for a DenseNet-style graph (the layer patterns of csrc/plan.cpp's lowering rules), images x
+def densenet_logits(model_path: str, x: np.ndarray, mode=None) -> np.ndarray:
+    """The reduced-precision engine's arithmetic (mode = E4m3Mode, the default, or Bf16Mode) for a DenseNet-style graph (the layer patterns of csrc/plan.cpp's lowering rules), images x
     [N,3,H,W] fp32 -> logits.  Stem: bf16 operands, fp32 accumulate, bias + ReLU -> e4m3; max-pool exact; dense layers and
     transitions as in the operator-level functions above; BN + ReLU + global average pool in fp32; classifier in fp32 (restated in
     double: its summation order is not part of the specification, the gate on the logits allows for it)."""
@@ -211,6 +211,7 @@ def densenet_e4m3_logits(model_path: str, x: np.ndarray) -> np.ndarray:
     if root not in sys.path:
         sys.path.insert(0, root)
     from tools import onnx_lite
+    M = mode or E4m3Mode
     g = onnx_lite.load(model_path).graph
     init = {k: np.asarray(v, dtype=np.float32) for k, v in g.initializers.items()}
     nodes = g.nodes
@@ -225,7 +226,7 @@ def densenet_e4m3_logits(model_path: str, x: np.ndarray) -> np.ndarray:
             w, b = init[n.inputs[1]], init[n.inputs[2]]
             acc = _conv_general(bf16(x), bf16(w), n.attrs["strides"][0], n.attrs["pads"][0])
             y = f32(acc + f32(b)[None, :, None, None])          # acc * 1.0 + bias, one fp32 FMA
-            env[nodes[i + 1].outputs[0]] = e4m3(np.maximum(y, 0.0))
+            env[nodes[i + 1].outputs[0]] = M.store(np.maximum(y, 0.0))
             i += 2
         elif op == "MaxPool":
             t = torch.nn.functional.max_pool2d(torch.from_numpy(env[n.inputs[0]]), n.attrs["kernel_shape"][0], n.attrs["strides"][0],
@@ -250,22 +251,30 @@ def densenet_e4m3_logits(model_path: str, x: np.ndarray) -> np.ndarray:
                 i += 5
                 continue
             assert nxt.op_type == "Conv" and nxt.attrs["kernel_shape"][0] == 1
-            wq, ws = quantise_weights(init[nxt.inputs[1]])
+            wq, ws = M.weights(init[nxt.inputs[1]])
             bias = init[nxt.inputs[2]] if len(nxt.inputs) > 2 else None
             after = nodes[i + 3]
             if after.op_type == "AveragePool":       # transition: pool commuted in front of the conv, pooled operand in f16
-                a = pooled_prologue_e4m3(xin, sc, sh, True)
-                env[after.outputs[0]] = epilogue_e4m3(conv_exact(a, wq, 0), ws, bias, False, out_mul=0.25)
+                a = M.pooled_prologue(xin, sc, sh, True)
+                env[after.outputs[0]] = M.epilogue(conv_exact(a, wq, 0), ws, bias, False, out_mul=0.25)
             else:
                 assert after.op_type == "Relu"
-                a = prologue_e4m3(xin, sc, sh, True)
-                env[after.outputs[0]] = epilogue_e4m3(conv_exact(a, wq, 0), ws, bias, True)
+                a = M.prologue(xin, sc, sh, True)
+                env[after.outputs[0]] = M.epilogue(conv_exact(a, wq, 0), ws, bias, True)
             i += 4
         elif op == "Conv":                            # the 3x3 conv of a dense layer
-            wq, ws = quantise_weights(init[n.inputs[1]])
+            wq, ws = M.weights(init[n.inputs[1]])
             bias = init[n.inputs[2]] if len(n.inputs) > 2 else None
-            env[n.outputs[0]] = epilogue_e4m3(conv_exact(env[n.inputs[0]], wq, n.attrs["pads"][0]), ws, bias, False)
+            env[n.outputs[0]] = M.epilogue(conv_exact(env[n.inputs[0]], wq, n.attrs["pads"][0]), ws, bias, False)
             i += 1
         else:
             raise NotImplementedError(f"{op} at node {i}")
     return env[g.outputs[0].name]
+
+
+def densenet_e4m3_logits(model_path: str, x: np.ndarray) -> np.ndarray:
+    return densenet_logits(model_path, x, E4m3Mode)
+
+
+def densenet_bf16_logits(model_path: str, x: np.ndarray) -> np.ndarray:
+    return densenet_logits(model_path, x, Bf16Mode)

@@ -351,6 +351,30 @@ def test_densenet_fp8_logits_match_the_engine_arithmetic_oracle(pkg, repo_dir, d
     assert np.array_equal(got.argmax(1), ref.argmax(1))
 
 
+def test_densenet_bf16_logits_match_the_engine_arithmetic_oracle(pkg, repo_dir, densenet_path, monkeypatch):
+    """The same whole-network check in BF16 mode (oracle/engine_arith.py densenet_bf16_logits).  bf16 steps are 16x finer than e4m3
+    steps, so the fp32 accumulator's summation order moves a few more stored values across a rounding boundary, but every such step
+    is 16x smaller too: the logits agree to 2e-3 .. 4e-3 of max|logit| on every image (the fp32 ONNX oracle is 3e-2 away); gate 1e-2
+    with identical top-5 classes in identical order."""
+    from oracle import engine_arith as ea
+    monkeypatch.setenv("B200_ENGINE_PRECISION", "bf16")
+    monkeypatch.setenv("B200_ENGINE_MAX_BATCH", "8")
+    monkeypatch.setenv("B200_ENGINE_INSTANCES", "1")
+    x = synth.to_model_input(synth.clustered_images_u8(4, start=300))
+    mgr = pkg.InferenceManager(repo_dir)
+    try:
+        mgr.load_model("densenet_onnx")
+        m = mgr.get_model("densenet_onnx")
+        got = m.infer([pkg.TensorData("data_0", x)], [pkg.OutputConfig("fc6_1", [4, 1000])])[0].data.astype(np.float64)
+    finally:
+        mgr.shutdown()
+    ref = ea.densenet_bf16_logits(densenet_path, x)
+    per_image = np.abs(got - ref).max(axis=1) / np.abs(ref).max()
+    print("bf16 DenseNet vs engine-arithmetic oracle, per image:", " ".join(f"{e:.1e}" for e in per_image))
+    assert per_image.max() < 1e-2, per_image
+    assert np.array_equal(np.argsort(-got, axis=1)[:, :5], np.argsort(-ref, axis=1)[:, :5])
+
+
 @pytest.mark.parametrize("precision", ["bf16", "fp8"])
 def test_densenet_low_precision_top5_agreement(pkg, repo_dir, densenet_path, monkeypatch, precision):
     n, chunk = 1024, 128
